@@ -1,0 +1,51 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
+//
+// A (activations) and W (nn.Linear weight layout, open_clip `in_proj_weight` / `c_fc.weight` ...) are
+// both K-major bf16, staged by TMA into 128B-swizzled shared-memory tiles and consumed by
+// tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BN x 16) with fp32 accumulators in TMEM.
+// Persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer,
+// warp 2 = TMEM allocator, warps 4..11 = epilogue (TMEM -> registers -> global).  Two TMEM
+// accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+#pragma once
+#include "common.cuh"
+
+namespace ec {
+
+enum GemmEpilogue : int {
+  EPI_BF16 = 0,        // out bf16 = acc + bias
+  EPI_BF16_GELU = 1,   // out bf16 = gelu(acc + bias)
+  EPI_F32 = 2,         // out f32  = acc + bias
+  EPI_F32_RESID = 3,   // out f32  = residual + acc + bias   (residual may alias out)
+  EPI_ARGMAX = 4       // vocab head: optional f32 logits + per-(row, column-slab) arg-max partials
+};
+
+struct GemmArgs {
+  const bf16* A;   int lda;       // [M, K], row stride lda elements (multiple of 8)
+  const bf16* W;   int ldw;       // [N, K], row stride ldw elements (multiple of 8)
+  int M, N, K;
+  const float* bias;              // [N] or nullptr
+  const float* residual; int ldr; // EPI_F32_RESID
+  void* out; int ldo;             // bf16 or f32 [M, ldo]
+  // EPI_ARGMAX only
+  float* logits; long long ld_logits;   // optional [M, N] f32 (may be nullptr)
+  long long logits_step_stride;         // logits base advances by (*cur_len - 1) * stride elements (0 if unused)
+  float* part_val; int* part_idx; int n_parts;  // [M, n_parts]; n_parts = gemm_argmax_parts(N)
+  int eos_col;                    // column forced to -inf when *cur_len < min_len
+  const int* cur_len; int min_len;
+  const int* skip_flag;           // device int; kernel returns immediately when *skip_flag != 0 (nullable)
+};
+
+// number of arg-max partial slots per row produced by EPI_ARGMAX for vocabulary size N
+int gemm_argmax_parts(int N);
+
+// Launch. Returns EC_OK or an error code (set_error() filled in).
+int gemm_bf16(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream);
+
+// Test / debug helper: plain SIMT reference GEMM with the same epilogues (used by the unit tests to
+// cross-check the tensor-core kernel on device; never called by the model path).
+int gemm_reference_simt(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream);
+
+// device-side watchdog flag (0 = fine). Reading it synchronises the stream.
+int gemm_check_watchdog(cudaStream_t stream);
+
+}  // namespace ec

@@ -1,0 +1,209 @@
+// LayerNorm and small row-wise kernels (HBM-bound, one warp per row, 128-bit accesses).
+#include "kernels.cuh"
+
+namespace ec {
+
+constexpr int kLnMaxVec = 8;   // 8 float4 per lane -> width <= 1024
+
+__device__ __forceinline__ void ln_stats(const float4 (&v)[kLnMaxVec], int nvec, int lane, int width, float& mean,
+                                         float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i)
+    if (lane + i * 32 < nvec) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  mean = warp_sum(s) / (float)width;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i)
+    if (lane + i * 32 < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  const float var = warp_sum(q) / (float)width;
+  rstd = 1.0f / sqrtf(var + 1e-5f);
+}
+
+template <bool kBf16Out>
+__device__ __forceinline__ void ln_store(const float4 (&v)[kLnMaxVec], int nvec, int lane, float mean, float rstd,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta, void* yrow) {
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (kBf16Out) {
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(yrow)[c] = pk;
+      } else {
+        reinterpret_cast<float4*>(yrow)[c] = o;
+      }
+    }
+  }
+}
+
+template <bool kBf16Out>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long ldx,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, void* __restrict__ y,
+                                                        long long ldy, int rows, int width,
+                                                        const int* __restrict__ skip_flag) {
+  if (skip_flag != nullptr && *skip_flag != 0) return;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = width >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
+  float4 v[kLnMaxVec];
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = lane + i * 32;
+    v[i] = (c < nvec) ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float mean, rstd;
+  ln_stats(v, nvec, lane, width, mean, rstd);
+  void* yrow = kBf16Out ? (void*)(reinterpret_cast<bf16*>(y) + (size_t)row * ldy)
+                        : (void*)(reinterpret_cast<float*>(y) + (size_t)row * ldy);
+  ln_store<kBf16Out>(v, nvec, lane, mean, rstd, gamma, beta, yrow);
+}
+
+int layernorm(const float* x, long long ldx, const float* gamma, const float* beta, void* y, long long ldy,
+              bool y_is_bf16, int rows, int width, const int* skip_flag, cudaStream_t stream) {
+  EC_REQUIRE(width % 4 == 0 && width <= kLnMaxVec * 128 && width > 0, EC_ERR_UNSUPPORTED,
+             "layernorm width %d unsupported (need multiple of 4, <= %d)", width, kLnMaxVec * 128);
+  EC_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, EC_ERR_INVALID, "layernorm strides must be multiples of 4");
+  if (rows <= 0) return EC_OK;
+  const int wpb = 8;
+  const int grid = ceil_div(rows, wpb);
+  if (y_is_bf16)
+    layernorm_kernel<true><<<grid, wpb * 32, 0, stream>>>(x, ldx, gamma, beta, y, ldy, rows, width, skip_flag);
+  else
+    layernorm_kernel<false><<<grid, wpb * 32, 0, stream>>>(x, ldx, gamma, beta, y, ldy, rows, width, skip_flag);
+  EC_CHECK_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vision_embed_ln_pre_kernel(const float* __restrict__ patch_emb,
+                                                                  const float* __restrict__ cls,
+                                                                  const float* __restrict__ pos,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta,
+                                                                  float* __restrict__ out, int batch, int tokens,
+                                                                  int width) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)batch * tokens) return;
+  const int b = (int)(row / tokens), t = (int)(row % tokens);
+  const int nvec = width >> 2;
+  const float4* src = (t == 0) ? reinterpret_cast<const float4*>(cls)
+                               : reinterpret_cast<const float4*>(patch_emb + ((size_t)b * (tokens - 1) + (t - 1)) * width);
+  const float4* pr = reinterpret_cast<const float4*>(pos + (size_t)t * width);
+  float4 v[kLnMaxVec];
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      const float4 a = src[c], p = __ldg(pr + c);
+      v[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  float mean, rstd;
+  ln_stats(v, nvec, lane, width, mean, rstd);
+  ln_store<false>(v, nvec, lane, mean, rstd, gamma, beta, out + (size_t)row * width);
+}
+
+int vision_embed_ln_pre(const float* patch_emb, const float* cls, const float* pos, const float* gamma,
+                        const float* beta, float* out, int batch, int tokens, int width, cudaStream_t stream) {
+  EC_REQUIRE(width % 4 == 0 && width <= kLnMaxVec * 128, EC_ERR_UNSUPPORTED, "vision width %d unsupported", width);
+  const long long rows = (long long)batch * tokens;
+  if (rows <= 0) return EC_OK;
+  const int wpb = 8;
+  vision_embed_ln_pre_kernel<<<(unsigned)ceil_div<long long>(rows, wpb), wpb * 32, 0, stream>>>(
+      patch_emb, cls, pos, gamma, beta, out, batch, tokens, width);
+  EC_CHECK_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) im2col_kernel(const bf16* __restrict__ img, bf16* __restrict__ out, int n,
+                                                     int size, int patch, int ld) {
+  const int grid_w = size / patch;
+  const int kdim = 3 * patch * patch;
+  const long long total = (long long)n * grid_w * grid_w * kdim;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % kdim);
+    const long long prow = i / kdim;
+    const int pidx = (int)(prow % (grid_w * grid_w));
+    const int b = (int)(prow / (grid_w * grid_w));
+    const int c = k / (patch * patch), rem = k % (patch * patch);
+    const int py = rem / patch, px = rem % patch;
+    const int gy = pidx / grid_w, gx = pidx % grid_w;
+    out[prow * ld + k] = img[(((size_t)b * 3 + c) * size + (gy * patch + py)) * size + gx * patch + px];
+  }
+}
+
+int im2col_patches(const bf16* img, bf16* out, int n, int size, int patch, int ld, cudaStream_t stream) {
+  EC_REQUIRE(size % patch == 0 && ld >= 3 * patch * patch, EC_ERR_INVALID, "im2col: bad geometry");
+  if (n <= 0) return EC_OK;
+  const long long total = (long long)n * (size / patch) * (size / patch) * 3 * patch * patch;
+  const int grid = (int)std::min<long long>(ceil_div<long long>(total, 256), (long long)num_sms() * 16);
+  im2col_kernel<<<grid, 256, 0, stream>>>(img, out, n, size, patch, ld);
+  EC_CHECK_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ x, long long ldx, float* __restrict__ y,
+                                                     long long ldy, int rows, int width) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * ldx;
+  float s = 0.f;
+  for (int c = lane; c < width; c += 32) s += xr[c] * xr[c];
+  s = warp_sum(s);
+  const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+  for (int c = lane; c < width; c += 32) y[(size_t)row * ldy + c] = xr[c] * inv;
+}
+
+int l2_normalize_rows(const float* x, long long ldx, float* y, long long ldy, int rows, int width,
+                      cudaStream_t stream) {
+  if (rows <= 0) return EC_OK;
+  l2norm_kernel<<<ceil_div(rows, 8), 256, 0, stream>>>(x, ldx, y, ldy, rows, width);
+  EC_CHECK_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+
+__global__ void __launch_bounds__(256) cvt_rows_kernel(const float* __restrict__ x, long long ldx, bf16* __restrict__ y,
+                                                       long long ldy, int rows, int width) {
+  const long long total = (long long)rows * width;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / width;
+    const int c = (int)(i % width);
+    y[r * ldy + c] = __float2bfloat16_rn(x[r * ldx + c]);
+  }
+}
+
+int convert_rows_f32_to_bf16(const float* x, long long ldx, bf16* y, long long ldy, int rows, int width,
+                             cudaStream_t stream) {
+  if (rows <= 0) return EC_OK;
+  const long long total = (long long)rows * width;
+  const int grid = (int)std::min<long long>(ceil_div<long long>(total, 256), (long long)num_sms() * 16);
+  cvt_rows_kernel<<<grid, 256, 0, stream>>>(x, ldx, y, ldy, rows, width);
+  EC_CHECK_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+
+}  // namespace ec

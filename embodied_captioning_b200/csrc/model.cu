@@ -1,0 +1,524 @@
+// CoCa captioner on B200: weight store + image tower + KV-cached greedy decoder orchestration.
+// Mirrors the wiring of the reference `CoCa` module (coca_model.py:92-203) and its `generate()` top-k path
+// (coca_model.py:205-333); the arithmetic of the towers is upstream open_clip's.
+#include "model.cuh"
+#include <cstring>
+#include <cstdlib>
+#include <string>
+
+namespace ec {
+
+// ---------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------
+static inline uint16_t f32_to_bf16_bits(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+  const uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;                                                          // round to nearest even
+  return (uint16_t)(u >> 16);
+}
+
+struct Bump {     // workspace carving, 256-byte aligned
+  unsigned char* base; size_t off = 0;
+  explicit Bump(void* b) : base(reinterpret_cast<unsigned char*>(b)) {}
+  template <typename T> T* take(size_t count) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += align_up(count * sizeof(T), 256);
+    return p;
+  }
+};
+
+int Model::upload_f32(const float* host, size_t n, float** dst) {
+  if (*dst == nullptr) EC_CHECK_CUDA(cudaMalloc(dst, std::max<size_t>(n, 4) * sizeof(float)));
+  EC_CHECK_CUDA(cudaMemcpy(*dst, host, n * sizeof(float), cudaMemcpyHostToDevice));
+  return EC_OK;
+}
+
+// host [rows, cols] fp32 (optionally transposed source [cols, rows]) -> device bf16 [rows, ld] at row offset
+int Model::upload_bf16(const float* host, int rows, int cols, bool src_transposed, bf16** dst, int total_rows, int ld,
+                       int row_off) {
+  if (*dst == nullptr) {
+    EC_CHECK_CUDA(cudaMalloc(dst, (size_t)total_rows * ld * sizeof(bf16)));
+    EC_CHECK_CUDA(cudaMemset(*dst, 0, (size_t)total_rows * ld * sizeof(bf16)));
+  }
+  std::vector<uint16_t> tmp((size_t)rows * ld, 0);
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c)
+      tmp[(size_t)r * ld + c] = f32_to_bf16_bits(src_transposed ? host[(size_t)c * rows + r] : host[(size_t)r * cols + c]);
+  EC_CHECK_CUDA(cudaMemcpy(*dst + (size_t)row_off * ld, tmp.data(), tmp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  return EC_OK;
+}
+
+Model::Model(const ec_config& c, int dev) : cfg(c), device(dev) {
+  vblocks.resize(c.vision_layers);
+  tblocks.resize(c.text_layers);
+  dself.resize(c.mm_layers);
+  dcross.resize(c.mm_layers);
+  patch_k = 3 * c.patch_size * c.patch_size;
+  patch_ld = (int)align_up((size_t)patch_k, 8);
+}
+
+Model::~Model() {
+  cudaSetDevice(device);
+  for (void* p : owned) cudaFree(p);
+  if (graph_exec) cudaGraphExecDestroy(graph_exec);
+  if (side_stream) cudaStreamDestroy(side_stream);
+  if (ev_in) cudaEventDestroy(ev_in);
+  if (ev_out) cudaEventDestroy(ev_out);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight loading by open_clip state-dict name
+// ---------------------------------------------------------------------------------------------------
+#define EC_EXPECT_NUMEL(expected)                                                                              \
+  EC_REQUIRE(numel == (int64_t)(expected), EC_ERR_INVALID, "tensor %s: expected %lld elements, got %lld", name, \
+             (long long)(expected), (long long)numel)
+
+int Model::set_block_tensor(Block& b, int width, const char* leaf, const char* name, const float* h, int64_t numel) {
+  auto vec = [&](float** dst, int n) -> int {
+    EC_EXPECT_NUMEL(n);
+    bool fresh = (*dst == nullptr);
+    EC_TRY(upload_f32(h, n, dst));
+    if (fresh) owned.push_back(*dst);
+    return EC_OK;
+  };
+  auto mat = [&](bf16** dst, int rows, int cols) -> int {
+    EC_EXPECT_NUMEL((int64_t)rows * cols);
+    bool fresh = (*dst == nullptr);
+    EC_TRY(upload_bf16(h, rows, cols, false, dst, rows, cols, 0));
+    if (fresh) owned.push_back(*dst);
+    return EC_OK;
+  };
+  const int W = width;
+  if (!strcmp(leaf, "ln_1.weight")) return vec(&b.ln1_g, W);
+  if (!strcmp(leaf, "ln_1.bias")) return vec(&b.ln1_b, W);
+  if (!strcmp(leaf, "ln_1_kv.weight")) return vec(&b.lnkv_g, W);
+  if (!strcmp(leaf, "ln_1_kv.bias")) return vec(&b.lnkv_b, W);
+  if (!strcmp(leaf, "ln_2.weight")) return vec(&b.ln2_g, W);
+  if (!strcmp(leaf, "ln_2.bias")) return vec(&b.ln2_b, W);
+  if (!strcmp(leaf, "attn.in_proj_weight")) return mat(&b.w_qkv, 3 * W, W);
+  if (!strcmp(leaf, "attn.in_proj_bias")) return vec(&b.b_qkv, 3 * W);
+  if (!strcmp(leaf, "attn.out_proj.weight")) return mat(&b.w_out, W, W);
+  if (!strcmp(leaf, "attn.out_proj.bias")) return vec(&b.b_out, W);
+  if (!strcmp(leaf, "mlp.c_fc.weight")) return mat(&b.w_fc1, 4 * W, W);
+  if (!strcmp(leaf, "mlp.c_fc.bias")) return vec(&b.b_fc1, 4 * W);
+  if (!strcmp(leaf, "mlp.c_proj.weight")) return mat(&b.w_fc2, W, 4 * W);
+  if (!strcmp(leaf, "mlp.c_proj.bias")) return vec(&b.b_fc2, W);
+  set_error("unknown block tensor %s", name);
+  return EC_ERR_INVALID;
+}
+
+int Model::set_tensor(const char* name, const float* h, int64_t numel) {
+  EC_CHECK_CUDA(cudaSetDevice(device));
+  const int W = cfg.vision_width, E = cfg.embed_dim, T = cfg.text_width, V = cfg.vocab_size;
+  finalized = false;
+  auto vec = [&](float** dst, int64_t n) -> int {
+    EC_EXPECT_NUMEL(n);
+    bool fresh = (*dst == nullptr);
+    EC_TRY(upload_f32(h, (size_t)n, dst));
+    if (fresh) owned.push_back(*dst);
+    return EC_OK;
+  };
+  auto mat = [&](bf16** dst, int rows, int cols, bool transposed, int total_rows, int ld, int row_off) -> int {
+    EC_EXPECT_NUMEL((int64_t)rows * cols);
+    bool fresh = (*dst == nullptr);
+    EC_TRY(upload_bf16(h, rows, cols, transposed, dst, total_rows, ld, row_off));
+    if (fresh) owned.push_back(*dst);
+    return EC_OK;
+  };
+  int layer = -1, consumed = 0;
+  if (!strcmp(name, "logit_scale")) return EC_OK;     // unused by the captioning path (coca_model.py:137,197)
+  if (sscanf(name, "visual.transformer.resblocks.%d.%n", &layer, &consumed) == 1 && consumed > 0) {
+    EC_REQUIRE(layer >= 0 && layer < cfg.vision_layers, EC_ERR_INVALID, "layer index out of range in %s", name);
+    return set_block_tensor(vblocks[layer], W, name + consumed, name, h, numel);
+  }
+  if (sscanf(name, "text.transformer.resblocks.%d.%n", &layer, &consumed) == 1 && consumed > 0) {
+    EC_REQUIRE(layer >= 0 && layer < cfg.text_layers, EC_ERR_INVALID, "layer index out of range in %s", name);
+    return set_block_tensor(tblocks[layer], T, name + consumed, name, h, numel);
+  }
+  if (sscanf(name, "text_decoder.resblocks.%d.%n", &layer, &consumed) == 1 && consumed > 0) {
+    EC_REQUIRE(layer >= 0 && layer < cfg.mm_layers, EC_ERR_INVALID, "layer index out of range in %s", name);
+    return set_block_tensor(dself[layer], T, name + consumed, name, h, numel);
+  }
+  if (sscanf(name, "text_decoder.cross_attn.%d.%n", &layer, &consumed) == 1 && consumed > 0) {
+    EC_REQUIRE(layer >= 0 && layer < cfg.mm_layers, EC_ERR_INVALID, "layer index out of range in %s", name);
+    return set_block_tensor(dcross[layer], T, name + consumed, name, h, numel);
+  }
+  if (!strcmp(name, "visual.conv1.weight")) return mat(&w_conv1, W, patch_k, false, W, patch_ld, 0);
+  if (!strcmp(name, "visual.class_embedding")) return vec(&cls_emb, W);
+  if (!strcmp(name, "visual.positional_embedding")) return vec(&vis_pos, (int64_t)(cfg_tokens()) * W);
+  if (!strcmp(name, "visual.ln_pre.weight")) return vec(&ln_pre_g, W);
+  if (!strcmp(name, "visual.ln_pre.bias")) return vec(&ln_pre_b, W);
+  if (!strcmp(name, "visual.attn_pool.query")) return vec(&pool_query, (int64_t)cfg.n_queries * E);
+  if (!strcmp(name, "visual.attn_pool.attn.q_proj_weight")) return mat(&w_pool_q, E, E, false, E, E, 0);
+  if (!strcmp(name, "visual.attn_pool.attn.k_proj_weight")) return mat(&w_pool_kv, E, W, false, 2 * E, W, 0);
+  if (!strcmp(name, "visual.attn_pool.attn.v_proj_weight")) return mat(&w_pool_kv, E, W, false, 2 * E, W, E);
+  if (!strcmp(name, "visual.attn_pool.attn.in_proj_bias")) return vec(&b_pool_qkv, 3 * E);
+  if (!strcmp(name, "visual.attn_pool.attn.out_proj.weight")) return mat(&w_pool_out, E, E, false, E, E, 0);
+  if (!strcmp(name, "visual.attn_pool.attn.out_proj.bias")) return vec(&b_pool_out, E);
+  if (!strcmp(name, "visual.attn_pool.ln_q.weight")) return vec(&ln_q_g, E);
+  if (!strcmp(name, "visual.attn_pool.ln_q.bias")) return vec(&ln_q_b, E);
+  if (!strcmp(name, "visual.attn_pool.ln_k.weight")) return vec(&ln_k_g, W);
+  if (!strcmp(name, "visual.attn_pool.ln_k.bias")) return vec(&ln_k_b, W);
+  if (!strcmp(name, "visual.ln_post.weight")) return vec(&ln_post_g, E);
+  if (!strcmp(name, "visual.ln_post.bias")) return vec(&ln_post_b, E);
+  if (!strcmp(name, "visual.proj")) return mat(&w_vproj, E, E, true, E, E, 0);          // pooled @ proj -> W = proj^T
+  if (!strcmp(name, "text.token_embedding.weight")) return vec(&tok_emb, (int64_t)V * T);
+  if (!strcmp(name, "text.positional_embedding")) return vec(&txt_pos, (int64_t)(cfg.context_length + 1) * T);
+  if (!strcmp(name, "text.cls_emb") || !strcmp(name, "text.ln_final.weight") || !strcmp(name, "text.ln_final.bias") ||
+      !strcmp(name, "text.text_projection"))
+    return EC_OK;   // only feed the pooled text latent, which generate() never consumes
+  if (!strcmp(name, "text_decoder.ln_final.weight")) return vec(&ln_final_g, T);
+  if (!strcmp(name, "text_decoder.ln_final.bias")) return vec(&ln_final_b, T);
+  if (!strcmp(name, "text_decoder.text_projection")) return mat(&w_vocab, V, T, true, V, T, 0);   // [T,V] -> [V,T]
+  set_error("unknown tensor name %s", name);
+  return EC_ERR_INVALID;
+}
+
+static bool block_complete(const Block& b, bool cross) {
+  return b.ln1_g && b.ln1_b && b.ln2_g && b.ln2_b && b.w_qkv && b.b_qkv && b.w_out && b.b_out && b.w_fc1 && b.b_fc1 &&
+         b.w_fc2 && b.b_fc2 && (!cross || (b.lnkv_g && b.lnkv_b));
+}
+
+int Model::finalize(cudaStream_t stream) {
+  EC_CHECK_CUDA(cudaSetDevice(device));
+  for (size_t i = 0; i < vblocks.size(); ++i)
+    EC_REQUIRE(block_complete(vblocks[i], false), EC_ERR_STATE, "visual block %zu incomplete", i);
+  for (size_t i = 0; i < tblocks.size(); ++i)
+    EC_REQUIRE(block_complete(tblocks[i], false), EC_ERR_STATE, "text block %zu incomplete", i);
+  for (size_t i = 0; i < dself.size(); ++i) {
+    EC_REQUIRE(block_complete(dself[i], false), EC_ERR_STATE, "decoder self block %zu incomplete", i);
+    EC_REQUIRE(block_complete(dcross[i], true), EC_ERR_STATE, "decoder cross block %zu incomplete", i);
+  }
+  EC_REQUIRE(w_conv1 && cls_emb && vis_pos && ln_pre_g && ln_pre_b && pool_query && w_pool_q && w_pool_kv &&
+                 b_pool_qkv && w_pool_out && b_pool_out && ln_q_g && ln_q_b && ln_k_g && ln_k_b && ln_post_g &&
+                 ln_post_b && w_vproj && tok_emb && txt_pos && ln_final_g && ln_final_b && w_vocab,
+             EC_ERR_STATE, "model tensors missing (load every open_clip CoCa tensor before finalize)");
+  // the pooler queries do not depend on the image: q = ln_q(query) @ Wq^T + bq, computed once
+  const int E = cfg.embed_dim, Q = cfg.n_queries;
+  bf16* lnq = nullptr;
+  EC_CHECK_CUDA(cudaMalloc(&lnq, (size_t)Q * E * sizeof(bf16)));
+  if (!pool_q_proj) {
+    EC_CHECK_CUDA(cudaMalloc(&pool_q_proj, (size_t)Q * E * sizeof(bf16)));
+    owned.push_back(pool_q_proj);
+  }
+  int rc = layernorm(pool_query, E, ln_q_g, ln_q_b, lnq, E, true, Q, E, nullptr, stream);
+  if (rc == EC_OK) {
+    GemmArgs g{};
+    g.A = lnq; g.lda = E; g.W = w_pool_q; g.ldw = E; g.M = Q; g.N = E; g.K = E; g.bias = b_pool_qkv;
+    g.out = pool_q_proj; g.ldo = E;
+    rc = gemm_bf16(g, EPI_BF16, stream);
+  }
+  cudaError_t e = cudaStreamSynchronize(stream);
+  cudaFree(lnq);
+  EC_TRY(rc);
+  EC_CHECK_CUDA(e);
+  EC_TRY(gemm_check_watchdog(stream));
+  finalized = true;
+  return EC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// transformer block helpers
+// ---------------------------------------------------------------------------------------------------
+static int linear(const bf16* A, int lda, const bf16* W, int ldw, const float* bias, int M, int N, int K, void* out,
+                  int ldo, GemmEpilogue epi, const float* resid, int ldr, const int* skip, cudaStream_t s) {
+  GemmArgs g{};
+  g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.M = M; g.N = N; g.K = K; g.bias = bias;
+  g.residual = resid; g.ldr = ldr; g.out = out; g.ldo = ldo; g.skip_flag = skip;
+  return gemm_bf16(g, epi, s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// image tower (coca_model.py:152-155 -> upstream VisionTransformer + AttentionalPooler)
+// ---------------------------------------------------------------------------------------------------
+struct EncodeWs {
+  bf16* patches; float* patch_emb; float* resid; bf16* ln; bf16* qkv; bf16* att; bf16* fc1;
+  bf16* pool_kv; bf16* pool_att; float* pool_out; bf16* pooled_bf16; float* pooled_proj;
+  size_t bytes;
+};
+
+static EncodeWs carve_encode(const Model& m, void* ws, int n) {
+  const ec_config& c = m.cfg;
+  const size_t G2 = (size_t)(c.image_size / c.patch_size) * (c.image_size / c.patch_size);
+  const size_t Mv = (size_t)n * (G2 + 1);
+  const size_t W = c.vision_width, E = c.embed_dim, Q = c.n_queries;
+  Bump b(ws);
+  EncodeWs w;
+  w.patches = b.take<bf16>((size_t)n * G2 * m.patch_ld);
+  w.patch_emb = b.take<float>((size_t)n * G2 * W);
+  w.resid = b.take<float>(Mv * W);
+  w.ln = b.take<bf16>(Mv * W);
+  w.qkv = b.take<bf16>(Mv * 3 * W);
+  w.att = b.take<bf16>(Mv * W);
+  w.fc1 = b.take<bf16>(Mv * 4 * W);
+  w.pool_kv = b.take<bf16>(Mv * 2 * E);
+  w.pool_att = b.take<bf16>((size_t)n * Q * E);
+  w.pool_out = b.take<float>((size_t)n * Q * E);
+  w.pooled_bf16 = b.take<bf16>((size_t)n * E);
+  w.pooled_proj = b.take<float>((size_t)n * E);
+  w.bytes = b.off;
+  return w;
+}
+
+size_t Model::encode_workspace_bytes(int n) const { return carve_encode(*this, nullptr, std::max(n, 1)).bytes; }
+
+// ln_post over the pooler output, split like `pooled, tokens = x[:,0], x[:,1:]`:
+// row (b, 0) -> bf16 pooled[b] (operand of the projection GEMM); row (b, q>0) -> f32 embs[b, q-1]
+__global__ void __launch_bounds__(256) ln_post_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, bf16* __restrict__ pooled,
+                                                            float* __restrict__ embs, int batch, int nq, int width) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)batch * nq) return;
+  const int b = (int)(row / nq), q = (int)(row % nq);
+  const float* xr = x + (size_t)row * width;
+  float s = 0.f;
+  for (int c = lane; c < width; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / (float)width;
+  float v = 0.f;
+  for (int c = lane; c < width; c += 32) { const float d = xr[c] - mean; v += d * d; }
+  const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)width + 1e-5f);
+  for (int c = lane; c < width; c += 32) {
+    const float y = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+    if (q == 0) pooled[(size_t)b * width + c] = __float2bfloat16_rn(y);
+    else if (embs != nullptr) embs[((size_t)b * (nq - 1) + (q - 1)) * width + c] = y;
+  }
+}
+
+int Model::encode_image(const bf16* x, int n, float* latent, float* embs, void* ws, size_t ws_bytes, cudaStream_t s) {
+  EC_REQUIRE(finalized, EC_ERR_STATE, "model not finalized");
+  EC_REQUIRE(n > 0, EC_ERR_INVALID, "encode_image: n = %d", n);
+  EC_CHECK_CUDA(cudaSetDevice(device));
+  const EncodeWs w = carve_encode(*this, ws, n);
+  EC_REQUIRE(ws_bytes >= w.bytes, EC_ERR_WORKSPACE, "encode workspace %zu < %zu", ws_bytes, w.bytes);
+  const int G = cfg.image_size / cfg.patch_size, G2 = G * G, TV = G2 + 1;
+  const int W = cfg.vision_width, E = cfg.embed_dim, Q = cfg.n_queries;
+  const int Mv = n * TV;
+  const int heads = W / cfg.vision_head_dim;
+
+  EC_TRY(im2col_patches(x, w.patches, n, cfg.image_size, cfg.patch_size, patch_ld, s));
+  EC_TRY(linear(w.patches, patch_ld, w_conv1, patch_ld, nullptr, n * G2, W, patch_k, w.patch_emb, W, EPI_F32, nullptr, 0,
+                nullptr, s));
+  EC_TRY(vision_embed_ln_pre(w.patch_emb, cls_emb, vis_pos, ln_pre_g, ln_pre_b, w.resid, n, TV, W, s));
+  for (int l = 0; l < cfg.vision_layers; ++l) {
+    const Block& b = vblocks[l];
+    EC_TRY(layernorm(w.resid, W, b.ln1_g, b.ln1_b, w.ln, W, true, Mv, W, nullptr, s));
+    EC_TRY(linear(w.ln, W, b.w_qkv, W, b.b_qkv, Mv, 3 * W, W, w.qkv, 3 * W, EPI_BF16, nullptr, 0, nullptr, s));
+    AttnArgs a{};
+    a.q = w.qkv; a.k = w.qkv + W; a.v = w.qkv + 2 * W;
+    a.q_bs = a.k_bs = a.v_bs = (long long)TV * 3 * W; a.q_rs = a.k_rs = a.v_rs = 3 * W;
+    a.o = w.att; a.o_bs = (long long)TV * W; a.o_rs = W;
+    a.batch = n; a.heads = heads; a.sq = TV; a.skv = TV; a.head_dim = cfg.vision_head_dim;
+    a.scale = 1.0f / sqrtf((float)cfg.vision_head_dim);
+    EC_TRY(attention_full(a, s));
+    EC_TRY(linear(w.att, W, b.w_out, W, b.b_out, Mv, W, W, w.resid, W, EPI_F32_RESID, w.resid, W, nullptr, s));
+    EC_TRY(layernorm(w.resid, W, b.ln2_g, b.ln2_b, w.ln, W, true, Mv, W, nullptr, s));
+    EC_TRY(linear(w.ln, W, b.w_fc1, W, b.b_fc1, Mv, 4 * W, W, w.fc1, 4 * W, EPI_BF16_GELU, nullptr, 0, nullptr, s));
+    EC_TRY(linear(w.fc1, 4 * W, b.w_fc2, 4 * W, b.b_fc2, Mv, W, 4 * W, w.resid, W, EPI_F32_RESID, w.resid, W, nullptr, s));
+  }
+  // attentional pooler: k = v = ln_k(x), q precomputed
+  EC_TRY(layernorm(w.resid, W, ln_k_g, ln_k_b, w.ln, W, true, Mv, W, nullptr, s));
+  EC_TRY(linear(w.ln, W, w_pool_kv, W, b_pool_qkv + E, Mv, 2 * E, W, w.pool_kv, 2 * E, EPI_BF16, nullptr, 0, nullptr, s));
+  {
+    const int hd = E / cfg.pooler_heads;
+    AttnArgs a{};
+    a.q = pool_q_proj; a.q_bs = 0; a.q_rs = E;
+    a.k = w.pool_kv; a.v = w.pool_kv + E; a.k_bs = a.v_bs = (long long)TV * 2 * E; a.k_rs = a.v_rs = 2 * E;
+    a.o = w.pool_att; a.o_bs = (long long)Q * E; a.o_rs = E;
+    a.batch = n; a.heads = cfg.pooler_heads; a.sq = Q; a.skv = TV; a.head_dim = hd;
+    a.scale = 1.0f / sqrtf((float)hd);
+    EC_TRY(attention_full(a, s));
+  }
+  EC_TRY(linear(w.pool_att, E, w_pool_out, E, b_pool_out, n * Q, E, E, w.pool_out, E, EPI_F32, nullptr, 0, nullptr, s));
+  {
+    const long long rows = (long long)n * Q;
+    ln_post_split_kernel<<<(unsigned)ceil_div<long long>(rows, 8), 256, 0, s>>>(w.pool_out, ln_post_g, ln_post_b,
+                                                                               w.pooled_bf16, embs, n, Q, E);
+    EC_CHECK_CUDA(cudaGetLastError());
+  }
+  if (latent != nullptr) {
+    EC_TRY(linear(w.pooled_bf16, E, w_vproj, E, nullptr, n, E, E, w.pooled_proj, E, EPI_F32, nullptr, 0, nullptr, s));
+    EC_TRY(l2_normalize_rows(w.pooled_proj, E, latent, E, n, E, s));
+  }
+  return EC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// decoder (coca_model.py:205-333 greedy path, KV-cached)
+// ---------------------------------------------------------------------------------------------------
+struct DecodeWs {
+  bf16* ln_kv; bf16* cross_kv; bf16* tk; bf16* tv; bf16* dk; bf16* dv;
+  float* x; bf16* ln; bf16* qkv; bf16* att; bf16* fc1; bf16* q;
+  float* part_val; int* part_idx; unsigned char* finished; DecodeState* st; int* tokens_tf;
+  size_t bytes;
+};
+
+static DecodeWs carve_decode(const Model& m, void* ws, int n, int seq_len) {
+  const ec_config& c = m.cfg;
+  const size_t T = c.text_width, NK = c.n_queries - 1;
+  const size_t L = seq_len;   // cache length (positions 0 .. seq_len-2 are ever written)
+  Bump b(ws);
+  DecodeWs w;
+  w.ln_kv = b.take<bf16>((size_t)n * NK * T);
+  w.cross_kv = b.take<bf16>((size_t)c.mm_layers * n * NK * 2 * T);
+  w.tk = b.take<bf16>((size_t)c.text_layers * n * L * T);
+  w.tv = b.take<bf16>((size_t)c.text_layers * n * L * T);
+  w.dk = b.take<bf16>((size_t)c.mm_layers * n * L * T);
+  w.dv = b.take<bf16>((size_t)c.mm_layers * n * L * T);
+  w.x = b.take<float>((size_t)n * T);
+  w.ln = b.take<bf16>((size_t)n * T);
+  w.qkv = b.take<bf16>((size_t)n * 3 * T);
+  w.att = b.take<bf16>((size_t)n * T);
+  w.fc1 = b.take<bf16>((size_t)n * 4 * T);
+  w.q = b.take<bf16>((size_t)n * T);
+  const size_t parts = (size_t)gemm_argmax_parts(c.vocab_size);
+  w.part_val = b.take<float>((size_t)n * parts);
+  w.part_idx = b.take<int>((size_t)n * parts);
+  w.finished = b.take<unsigned char>((size_t)n);
+  w.st = b.take<DecodeState>(1);
+  w.tokens_tf = b.take<int>((size_t)n * L);
+  w.bytes = b.off;
+  return w;
+}
+
+size_t Model::decode_workspace_bytes(int n, int seq_len) const {
+  return carve_decode(*this, nullptr, std::max(n, 1), std::max(seq_len, 2)).bytes;
+}
+
+int Model::self_block(const Block& b, const DecodeWs& w, bf16* kc, bf16* vc, int n, int max_len, int heads,
+                      cudaStream_t s) {
+  const int T = cfg.text_width;
+  const int* skip = &w.st->done;
+  EC_TRY(layernorm(w.x, T, b.ln1_g, b.ln1_b, w.ln, T, true, n, T, skip, s));
+  EC_TRY(linear(w.ln, T, b.w_qkv, T, b.b_qkv, n, 3 * T, T, w.qkv, 3 * T, EPI_BF16, nullptr, 0, skip, s));
+  EC_TRY(decode_self_attention(w.qkv, kc, vc, w.att, n, heads, T / heads, max_len, w.finished, w.st, s));
+  EC_TRY(linear(w.att, T, b.w_out, T, b.b_out, n, T, T, w.x, T, EPI_F32_RESID, w.x, T, skip, s));
+  EC_TRY(layernorm(w.x, T, b.ln2_g, b.ln2_b, w.ln, T, true, n, T, skip, s));
+  EC_TRY(linear(w.ln, T, b.w_fc1, T, b.b_fc1, n, 4 * T, T, w.fc1, 4 * T, EPI_BF16_GELU, nullptr, 0, skip, s));
+  EC_TRY(linear(w.fc1, 4 * T, b.w_fc2, 4 * T, b.b_fc2, n, T, 4 * T, w.x, T, EPI_F32_RESID, w.x, T, skip, s));
+  return EC_OK;
+}
+
+int Model::cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int n, cudaStream_t s) {
+  const int T = cfg.text_width, NK = cfg.n_queries - 1;
+  const int* skip = &w.st->done;
+  EC_TRY(layernorm(w.x, T, b.ln1_g, b.ln1_b, w.ln, T, true, n, T, skip, s));
+  EC_TRY(linear(w.ln, T, b.w_qkv, T, b.b_qkv, n, T, T, w.q, T, EPI_BF16, nullptr, 0, skip, s));   // q rows only
+  EC_TRY(decode_cross_attention(w.q, kv, w.att, n, cfg.mm_heads, T / cfg.mm_heads, NK, w.finished, w.st, s));
+  EC_TRY(linear(w.att, T, b.w_out, T, b.b_out, n, T, T, w.x, T, EPI_F32_RESID, w.x, T, skip, s));
+  EC_TRY(layernorm(w.x, T, b.ln2_g, b.ln2_b, w.ln, T, true, n, T, skip, s));
+  EC_TRY(linear(w.ln, T, b.w_fc1, T, b.b_fc1, n, 4 * T, T, w.fc1, 4 * T, EPI_BF16_GELU, nullptr, 0, skip, s));
+  EC_TRY(linear(w.fc1, 4 * T, b.w_fc2, 4 * T, b.b_fc2, n, T, 4 * T, w.x, T, EPI_F32_RESID, w.x, T, skip, s));
+  return EC_OK;
+}
+
+// one decoder step for all crops: token at position cur_len-1 in, token cur_len out
+int Model::decode_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int seq_len, int min_len, float* logits,
+                       bool teacher_forced, cudaStream_t s) {
+  const int T = cfg.text_width, NK = cfg.n_queries - 1, V = cfg.vocab_size;
+  const size_t cache_layer = (size_t)n * seq_len * T;
+  EC_TRY(decode_embed(tokens, ld_tokens, tok_emb, txt_pos, w.x, n, T, w.st, s));
+  for (int l = 0; l < cfg.text_layers; ++l)
+    EC_TRY(self_block(tblocks[l], w, w.tk + l * cache_layer, w.tv + l * cache_layer, n, seq_len, cfg.text_heads, s));
+  for (int l = 0; l < cfg.mm_layers; ++l) {
+    EC_TRY(self_block(dself[l], w, w.dk + l * cache_layer, w.dv + l * cache_layer, n, seq_len, cfg.mm_heads, s));
+    EC_TRY(cross_block(dcross[l], w, w.cross_kv + (size_t)l * n * NK * 2 * T, n, s));
+  }
+  EC_TRY(layernorm(w.x, T, ln_final_g, ln_final_b, w.ln, T, true, n, T, &w.st->done, s));
+  GemmArgs g{};
+  g.A = w.ln; g.lda = T; g.W = w_vocab; g.ldw = T; g.M = n; g.N = V; g.K = T;
+  g.logits = logits; g.ld_logits = V; g.logits_step_stride = (long long)n * V;
+  g.part_val = w.part_val; g.part_idx = w.part_idx; g.n_parts = gemm_argmax_parts(V);
+  g.eos_col = teacher_forced ? -1 : cfg.eos_token_id; g.cur_len = &w.st->cur_len; g.min_len = min_len;
+  g.skip_flag = &w.st->done;
+  EC_TRY(gemm_bf16(g, EPI_ARGMAX, s));
+  if (!teacher_forced)
+    EC_TRY(decode_select(w.part_val, w.part_idx, g.n_parts, tokens, ld_tokens, w.finished, n, seq_len,
+                         cfg.eos_token_id, cfg.pad_token_id, w.st, s));
+  EC_TRY(decode_advance(w.st, teacher_forced, n, s));
+  return EC_OK;
+}
+
+int Model::prefill_cross_kv(const DecodeWs& w, const float* embs, int n, cudaStream_t s) {
+  const int T = cfg.text_width, NK = cfg.n_queries - 1;
+  const int rows = n * NK;
+  for (int l = 0; l < cfg.mm_layers; ++l) {
+    const Block& b = dcross[l];
+    EC_TRY(layernorm(embs, T, b.lnkv_g, b.lnkv_b, w.ln_kv, T, true, rows, T, nullptr, s));
+    EC_TRY(linear(w.ln_kv, T, b.w_qkv + (size_t)T * T, T, b.b_qkv + T, rows, 2 * T, T,
+                  w.cross_kv + (size_t)l * rows * 2 * T, 2 * T, EPI_BF16, nullptr, 0, nullptr, s));
+  }
+  return EC_OK;
+}
+
+int Model::run_steps(const DecodeWs& w, int* tokens, int ld_tokens, int n, int seq_len, int min_len, float* logits,
+                     bool teacher_forced, int steps, cudaStream_t s) {
+  if (!use_graph) {
+    for (int t = 0; t < steps; ++t) EC_TRY(decode_step(w, tokens, ld_tokens, n, seq_len, min_len, logits, teacher_forced, s));
+    return EC_OK;
+  }
+  // CUDA-graph path: capture one step on a private stream (the caller's stream may be the legacy default
+  // stream, which cannot be captured), replay it `steps` times; re-capture only when the launch set changes.
+  if (!side_stream) {
+    EC_CHECK_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+    EC_CHECK_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+    EC_CHECK_CUDA(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
+  }
+  GraphKey key{w.x, tokens, logits, n, seq_len, min_len, ld_tokens, teacher_forced ? 1 : 0};
+  if (!graph_exec || memcmp(&key, &graph_key, sizeof(GraphKey)) != 0) {
+    if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    EC_CHECK_CUDA(cudaStreamBeginCapture(side_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = decode_step(w, tokens, ld_tokens, n, seq_len, min_len, logits, teacher_forced, side_stream);
+    cudaError_t ce = cudaStreamEndCapture(side_stream, &graph);
+    if (rc != EC_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    EC_CHECK_CUDA(ce);
+    ce = cudaGraphInstantiate(&graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    EC_CHECK_CUDA(ce);
+    graph_key = key;
+  }
+  EC_CHECK_CUDA(cudaEventRecord(ev_in, s));
+  EC_CHECK_CUDA(cudaStreamWaitEvent(side_stream, ev_in, 0));
+  for (int t = 0; t < steps; ++t) EC_CHECK_CUDA(cudaGraphLaunch(graph_exec, side_stream));
+  EC_CHECK_CUDA(cudaEventRecord(ev_out, side_stream));
+  EC_CHECK_CUDA(cudaStreamWaitEvent(s, ev_out, 0));
+  return EC_OK;
+}
+
+int Model::decode_greedy(const float* embs, int n, int seq_len, int min_len, int* tokens, float* logits, void* ws,
+                         size_t ws_bytes, cudaStream_t s) {
+  EC_REQUIRE(finalized, EC_ERR_STATE, "model not finalized");
+  EC_REQUIRE(n > 0, EC_ERR_INVALID, "decode_greedy: n = %d", n);
+  EC_REQUIRE(seq_len > min_len, EC_ERR_INVALID, "seq_len must be larger than min_seq_len");   // coca_model.py:228
+  EC_REQUIRE(seq_len <= cfg.context_length + 1, EC_ERR_UNSUPPORTED, "seq_len %d exceeds the positional table (%d)",
+             seq_len, cfg.context_length + 1);
+  EC_CHECK_CUDA(cudaSetDevice(device));
+  const DecodeWs w = carve_decode(*this, ws, n, seq_len);
+  EC_REQUIRE(ws_bytes >= w.bytes, EC_ERR_WORKSPACE, "decode workspace %zu < %zu", ws_bytes, w.bytes);
+  EC_TRY(prefill_cross_kv(w, embs, n, s));
+  EC_TRY(decode_init(tokens, seq_len, w.finished, n, seq_len, cfg.sot_token_id, cfg.pad_token_id, w.st, s));
+  return run_steps(w, tokens, seq_len, n, seq_len, min_len, logits, false, seq_len - 1, s);
+}
+
+int Model::forward_logits(const float* embs, const int* text, int n, int t, float* logits, void* ws, size_t ws_bytes,
+                          cudaStream_t s) {
+  EC_REQUIRE(finalized, EC_ERR_STATE, "model not finalized");
+  EC_REQUIRE(n > 0 && t > 0 && logits != nullptr, EC_ERR_INVALID, "forward_logits: bad arguments");
+  EC_REQUIRE(t <= cfg.context_length, EC_ERR_UNSUPPORTED, "text length %d exceeds context %d", t, cfg.context_length);
+  EC_CHECK_CUDA(cudaSetDevice(device));
+  const int L = t + 1;
+  const DecodeWs w = carve_decode(*this, ws, n, L);
+  EC_REQUIRE(ws_bytes >= w.bytes, EC_ERR_WORKSPACE, "decode workspace %zu < %zu", ws_bytes, w.bytes);
+  EC_TRY(prefill_cross_kv(w, embs, n, s));
+  // teacher forcing: the step engine reads its input token from a [n, L] table holding the given text
+  EC_TRY(decode_init(w.tokens_tf, L, w.finished, n, L, cfg.sot_token_id, cfg.pad_token_id, w.st, s));
+  EC_CHECK_CUDA(cudaMemcpy2DAsync(w.tokens_tf, (size_t)L * sizeof(int), text, (size_t)t * sizeof(int),
+                                  (size_t)t * sizeof(int), n, cudaMemcpyDeviceToDevice, s));
+  return run_steps(w, w.tokens_tf, L, n, L, 0, logits, true, t, s);
+}
+
+}  // namespace ec

@@ -1,0 +1,86 @@
+// Model object behind the opaque `ec_model` handle of include/ec_b200.h.
+#pragma once
+#include <vector>
+#include "common.cuh"
+#include "gemm_sm100.cuh"
+#include "kernels.cuh"
+#include "../../include/ec_b200.h"
+
+namespace ec {
+
+struct Block {   // one open_clip ResidualAttentionBlock
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr, *lnkv_g = nullptr, *lnkv_b = nullptr;
+  bf16 *w_qkv = nullptr, *w_out = nullptr, *w_fc1 = nullptr, *w_fc2 = nullptr;     // nn.Linear layout [out, in]
+  float *b_qkv = nullptr, *b_out = nullptr, *b_fc1 = nullptr, *b_fc2 = nullptr;
+};
+
+struct DecodeWs;
+
+struct GraphKey { const void* ws; const void* tokens; const void* logits; int n, seq_len, min_len, ld, tf; };
+
+struct Model {
+  ec_config cfg;
+  int device;
+  bool finalized = false;
+  bool use_graph = false;
+  int patch_k = 0, patch_ld = 0;
+
+  // vision tower
+  bf16* w_conv1 = nullptr;
+  float *cls_emb = nullptr, *vis_pos = nullptr, *ln_pre_g = nullptr, *ln_pre_b = nullptr;
+  std::vector<Block> vblocks;
+  // attentional pooler
+  float* pool_query = nullptr;
+  bf16 *w_pool_q = nullptr, *w_pool_kv = nullptr, *w_pool_out = nullptr, *w_vproj = nullptr, *pool_q_proj = nullptr;
+  float *b_pool_qkv = nullptr, *b_pool_out = nullptr;
+  float *ln_q_g = nullptr, *ln_q_b = nullptr, *ln_k_g = nullptr, *ln_k_b = nullptr, *ln_post_g = nullptr,
+        *ln_post_b = nullptr;
+  // text tower + multimodal decoder
+  float *tok_emb = nullptr, *txt_pos = nullptr;
+  std::vector<Block> tblocks, dself, dcross;
+  float *ln_final_g = nullptr, *ln_final_b = nullptr;
+  bf16* w_vocab = nullptr;
+
+  std::vector<void*> owned;
+  // CUDA-graph replay of the decoder step
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  GraphKey graph_key{};
+
+  Model(const ec_config& c, int dev);
+  ~Model();
+  int cfg_tokens() const { return (cfg.image_size / cfg.patch_size) * (cfg.image_size / cfg.patch_size) + 1; }
+
+  int set_tensor(const char* name, const float* host, int64_t numel);
+  int finalize(cudaStream_t stream);
+
+  size_t encode_workspace_bytes(int n) const;
+  int encode_image(const bf16* x, int n, float* latent, float* embs, void* ws, size_t ws_bytes, cudaStream_t s);
+
+  size_t decode_workspace_bytes(int n, int seq_len) const;
+  int decode_greedy(const float* embs, int n, int seq_len, int min_len, int* tokens, float* logits, void* ws,
+                    size_t ws_bytes, cudaStream_t s);
+  int forward_logits(const float* embs, const int* text, int n, int t, float* logits, void* ws, size_t ws_bytes,
+                     cudaStream_t s);
+
+ private:
+  int upload_f32(const float* host, size_t n, float** dst);
+  int upload_bf16(const float* host, int rows, int cols, bool src_transposed, bf16** dst, int total_rows, int ld,
+                  int row_off);
+  int set_block_tensor(Block& b, int width, const char* leaf, const char* name, const float* h, int64_t numel);
+  int self_block(const Block& b, const DecodeWs& w, bf16* kc, bf16* vc, int n, int max_len, int heads, cudaStream_t s);
+  int cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int n, cudaStream_t s);
+  int decode_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int seq_len, int min_len, float* logits,
+                  bool teacher_forced, cudaStream_t s);
+  int prefill_cross_kv(const DecodeWs& w, const float* embs, int n, cudaStream_t s);
+  int run_steps(const DecodeWs& w, int* tokens, int ld_tokens, int n, int seq_len, int min_len, float* logits,
+                bool teacher_forced, int steps, cudaStream_t s);
+};
+
+}  // namespace ec
+
+struct ec_model {
+  ec::Model impl;
+  ec_model(const ec_config& c, int dev) : impl(c, dev) {}
+};

@@ -1,0 +1,140 @@
+"""Torch-tensor front-ends of the exported kernels (thin: argument checking + ctypes call).
+
+PyTorch only owns the device memory and the stream here; every operation runs in `libec_b200.so`.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+EPI_BF16, EPI_BF16_GELU, EPI_F32, EPI_F32_RESID = 0, 1, 2, 3
+MODE_FULL_MEAN_1MINUS, MODE_PAIRS_MEAN_COS = 0, 1
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _check_dev(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise nat.NativeError("expected CUDA tensors (there is no CPU path)")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = EPI_BF16,
+         residual: Optional[torch.Tensor] = None, simt_reference: bool = False) -> torch.Tensor:
+    """out[M,N] = a[M,K] @ w[N,K]^T (+bias) with the fused epilogue; a, w bf16 row-major."""
+    _check_dev(a, w, bias, residual)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), device=a.device, dtype=torch.bfloat16 if epilogue in (EPI_BF16, EPI_BF16_GELU)
+                      else torch.float32)
+    with torch.cuda.device(a.device):
+        nat.check(nat.lib().ec_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, nat.ptr(bias),
+                                         nat.ptr(residual), residual.stride(0) if residual is not None else 0,
+                                         out.data_ptr(), out.stride(0), epilogue, int(simt_reference), _stream(a)),
+                  "ec_gemm_bf16")
+    return out
+
+
+def gemm_argmax(a: torch.Tensor, w: torch.Tensor, want_logits: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    _check_dev(a, w)
+    M, K = a.shape
+    N = w.shape[0]
+    logits = torch.empty((M, N), device=a.device, dtype=torch.float32) if want_logits else None
+    arg = torch.empty((M,), device=a.device, dtype=torch.int32)
+    parts = (N + 255) // 256 * 2
+    ws = torch.empty((M * parts * 8 + 512,), device=a.device, dtype=torch.uint8)
+    with torch.cuda.device(a.device):
+        nat.check(nat.lib().ec_gemm_argmax(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K,
+                                           nat.ptr(logits), arg.data_ptr(), ws.data_ptr(), ws.numel(), _stream(a)),
+                  "ec_gemm_argmax")
+    return arg, logits
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_bf16: bool = True) -> torch.Tensor:
+    _check_dev(x, gamma, beta)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    rows, width = x.shape
+    y = torch.empty((rows, width), device=x.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    with torch.cuda.device(x.device):
+        nat.check(nat.lib().ec_layernorm(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                         y.stride(0), int(out_bf16), rows, width, _stream(x)), "ec_layernorm")
+    return y
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
+    """q [B,Sq,H*D] (or [Sq,H*D] shared by the batch), k/v [B,Skv,H*D] bf16 -> [B,Sq,H*D] bf16."""
+    _check_dev(q, k, v)
+    B, Skv, C = k.shape
+    D = C // heads
+    if q.dim() == 2:
+        q_bs, Sq = 0, q.shape[0]
+        q_rs = q.stride(0)
+    else:
+        q_bs, Sq, q_rs = q.stride(0), q.shape[1], q.stride(1)
+    out = torch.empty((B, Sq, C), device=k.device, dtype=torch.bfloat16)
+    with torch.cuda.device(k.device):
+        nat.check(nat.lib().ec_attention(q.data_ptr(), q_bs, q_rs, k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(),
+                                         v.stride(0), v.stride(1), out.data_ptr(), out.stride(0), out.stride(1), B,
+                                         heads, Sq, Skv, D, _stream(k)), "ec_attention")
+    return out
+
+
+def preprocess_crops(frames: torch.Tensor, rects: torch.Tensor, frame_idx: torch.Tensor,
+                     flags: Optional[torch.Tensor] = None, size: int = 224, want_f32: bool = False,
+                     want_bf16: bool = True):
+    """frames uint8 [F,H,W,C] on device; rects int32 [N,4]; -> (bf16 [N,3,S,S] | None, f32 | None, status int32 [N])."""
+    _check_dev(frames, rects, frame_idx, flags)
+    assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.is_contiguous()
+    assert rects.dtype == torch.int32 and rects.is_contiguous() and frame_idx.dtype == torch.int32
+    N = rects.shape[0]
+    F_, H, W, Cc = frames.shape
+    dev = frames.device
+    out_bf16 = torch.empty((N, 3, size, size), device=dev, dtype=torch.bfloat16) if want_bf16 else None
+    out_f32 = torch.empty((N, 3, size, size), device=dev, dtype=torch.float32) if want_f32 else None
+    status = torch.zeros((max(N, 1),), device=dev, dtype=torch.int32)
+    lib = nat.lib()
+    with torch.cuda.device(dev):
+        for s in range(0, N, 32768):      # grid.y limit
+            e = min(N, s + 32768)
+            nat.check(lib.ec_preprocess_crops(
+                frames.data_ptr(), F_, H, W, Cc, rects[s:e].data_ptr(), frame_idx[s:e].data_ptr(),
+                None if flags is None else flags[s:e].data_ptr(), e - s, size,
+                None if out_bf16 is None else out_bf16[s:e].data_ptr(),
+                None if out_f32 is None else out_f32[s:e].data_ptr(), status[s:e].data_ptr(), _stream(frames)),
+                "ec_preprocess_crops")
+    return out_bf16, out_f32, status[:N]
+
+
+def instance_disagreement(emb: torch.Tensor, keys: torch.Tensor, mode: int = MODE_FULL_MEAN_1MINUS):
+    """emb f32 [N,D], keys int64 [N] on device -> (keys[M] int64, score[M] f32, count[M] int32), key-sorted."""
+    _check_dev(emb, keys)
+    assert emb.dtype == torch.float32 and emb.dim() == 2 and emb.stride(1) == 1
+    assert keys.dtype == torch.int64 and keys.is_contiguous()
+    N, D = emb.shape
+    dev = emb.device
+    ok = torch.empty((max(N, 1),), device=dev, dtype=torch.int64)
+    sc = torch.empty((max(N, 1),), device=dev, dtype=torch.float32)
+    ct = torch.empty((max(N, 1),), device=dev, dtype=torch.int32)
+    m = torch.zeros((1,), device=dev, dtype=torch.int32)
+    lib = nat.lib()
+    wsb = lib.ec_disagreement_workspace_bytes(N)
+    ws = torch.empty((max(wsb, 16),), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        nat.check(lib.ec_instance_disagreement(emb.data_ptr(), emb.stride(0), keys.data_ptr(), N, D, mode, ok.data_ptr(),
+                                               sc.data_ptr(), ct.data_ptr(), m.data_ptr(), ws.data_ptr(), ws.numel(),
+                                               _stream(emb)), "ec_instance_disagreement")
+    M = int(m.item())
+    return ok[:M], sc[:M], ct[:M]
+
+
+def check_watchdog(device=None):
+    with torch.cuda.device(device):
+        nat.check(nat.lib().ec_check_watchdog(torch.cuda.current_stream(device).cuda_stream), "ec_check_watchdog")

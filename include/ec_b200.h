@@ -1,0 +1,121 @@
+/*
+ * libec_b200 -- C ABI of the B200-native captioner hot path (sm_100a only).
+ *
+ * The reference (hsp-iit/embodied-captioning) has no FFI layer: its boundary for this path is a Python object
+ * protocol.  Each entry point below names the reference interface it stands behind;
+ * the Python shims in `embodied_captioning_b200/captioner/` keep those names and call these symbols through
+ * ctypes on torch-owned device pointers.
+ *
+ * Conventions: every function returns 0 (EC_OK) or a negative EC_ERR_* code; `ec_last_error()` returns a
+ * thread-local message.  All pointers named *_dev are device pointers on the model's device; `stream` is a
+ * cudaStream_t passed as void*.  Hot calls never allocate: the caller passes a workspace of at least
+ * `ec_*_workspace_bytes()` bytes.  Nothing here falls back to the CPU; a non-sm_100 device is EC_ERR_DEVICE.
+ */
+#ifndef EC_B200_H_
+#define EC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EC_OK 0
+#define EC_ERR_INVALID (-1)
+#define EC_ERR_CUDA (-2)
+#define EC_ERR_UNSUPPORTED (-3)
+#define EC_ERR_WORKSPACE (-4)
+#define EC_ERR_STATE (-5)
+#define EC_ERR_DEVICE (-6)
+#define EC_ERR_TIMEOUT (-7)
+
+#define EC_ABI_VERSION 1
+
+/* Architecture hyper-parameters; mirrors the JSON registry read by
+ * experimenting_env/captioner/models/coca/factory.py:27-57 (model_configs/coca_ViT-L-14.json). */
+typedef struct ec_config {
+  int32_t embed_dim, image_size, patch_size;
+  int32_t vision_width, vision_layers, vision_head_dim;
+  int32_t pooler_heads, n_queries;
+  int32_t text_width, text_heads, text_layers;
+  int32_t mm_layers, mm_heads;
+  int32_t context_length, vocab_size;
+  int32_t sot_token_id, eos_token_id, pad_token_id;
+} ec_config;
+
+typedef struct ec_model ec_model;
+
+int ec_abi_version(void);
+const char* ec_last_error(void);
+
+/* ---- model lifetime: replaces `create_model_and_transforms(...)` (factory.py:378-432) + `load_checkpoint`
+ * (factory.py:131-180).  Tensors are passed by their open_clip state-dict names as host fp32 arrays. */
+int ec_model_create(const ec_config* cfg, int device, ec_model** out);
+int ec_model_destroy(ec_model* m);
+int ec_model_set_tensor(ec_model* m, const char* name, const float* host_data, int64_t numel);
+int ec_model_finalize(ec_model* m, void* stream);   /* checks completeness, pre-computes the pooler queries */
+int ec_model_set_option(ec_model* m, const char* key, int value);   /* "decode_graph": 0/1 */
+
+/* ---- crop + image transform: replaces `self.preprocess(PIL.Image)` at coca.py:28 (upstream
+ * image_transform_v2) applied to the crops cut at goal_exploration.py:95-99 / pseudolabeler.py:670-675 /
+ * evaluate_finetuned_model.py:33-37.  rects are integer source rectangles already computed by the box policy. */
+int ec_preprocess_crops(const uint8_t* frames_dev, int32_t n_frames, int32_t frame_h, int32_t frame_w,
+                        int32_t frame_c, const int32_t* rects_dev, const int32_t* frame_idx_dev,
+                        const int32_t* flags_dev, int32_t n, int32_t out_size, void* out_bf16_dev,
+                        float* out_f32_dev, int32_t* status_dev, void* stream);
+
+/* ---- image tower: replaces `CoCa._encode_image` (coca_model.py:152-155). x: bf16 [n,3,S,S];
+ * latent: f32 [n,E] (L2-normalised); embs: f32 [n, n_queries-1, E]. */
+size_t ec_encode_workspace_bytes(const ec_model* m, int32_t n);
+int ec_encode_image(ec_model* m, const void* x_bf16_dev, int32_t n, float* latent_dev, float* embs_dev, void* ws_dev,
+                    size_t ws_bytes, void* stream);
+
+/* ---- greedy decoder: replaces `CoCa.generate(..., generation_type='top_k')` with top_k=1
+ * (coca_model.py:205-333, called at coca.py:29 and evaluate_finetuned_model.py:43).
+ * tokens: int32 [n, seq_len] (col 0 = SOT, PAD after EOS); logits (optional): f32 [seq_len-1, n, vocab],
+ * row b of step t valid while crop b was still active; n_steps_host (optional, host int): number of
+ * columns the reference loop would have produced (it stops once every crop has emitted EOS). */
+size_t ec_decode_workspace_bytes(const ec_model* m, int32_t n, int32_t seq_len);
+int ec_decode_greedy(ec_model* m, const float* embs_dev, int32_t n, int32_t seq_len, int32_t min_seq_len,
+                     int32_t* tokens_dev, float* logits_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* ---- teacher-forced logits: replaces `CoCa.forward(image, text, image_embs=...)` (coca_model.py:170-203)
+ * for output_labels=False: text int32 [n, t] -> logits f32 [t, n, vocab] (step-major; the shim permutes). */
+int ec_forward_logits(ec_model* m, const float* embs_dev, const int32_t* text_dev, int32_t n, int32_t t,
+                      float* logits_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* ---- per-instance disagreement: replaces the dict-comprehension over `_cosine_distance`
+ * (projection_utils.py:743-754, 928-942; mode 0) and `mean_cosine_similarity`
+ * (scripts/compute_cosine_sim.py:11-22; mode 1) grouped by instance key (pseudocaptioner.py:137). */
+size_t ec_disagreement_workspace_bytes(int32_t n);
+int ec_instance_disagreement(const float* emb_dev, int64_t ld_emb, const int64_t* keys_dev, int32_t n, int32_t d,
+                             int32_t mode, int64_t* out_keys_dev, float* out_score_dev, int32_t* out_count_dev,
+                             int32_t* out_m_dev, void* ws_dev, size_t ws_bytes, void* stream);
+/* multi-GPU form: rows live in `world` peer-mapped buffers (row i in peers[i / rows_per_rank]); this rank
+ * reduces the instances m with m % part_world == part_rank and writes 0 for the others. */
+int ec_instance_disagreement_peers(const float* const* peers_dev, int32_t world, int32_t rows_per_rank,
+                                   int64_t ld_emb, const int64_t* keys_dev, int32_t n, int32_t d, int32_t mode,
+                                   int32_t part_rank, int32_t part_world, int64_t* out_keys_dev,
+                                   float* out_score_dev, int32_t* out_count_dev, int32_t* out_m_dev, void* ws_dev,
+                                   size_t ws_bytes, void* stream);
+
+/* ---- building blocks exported for unit tests and micro-benchmarks (same kernels the model path launches) */
+int ec_gemm_bf16(const void* a_bf16_dev, int32_t lda, const void* w_bf16_dev, int32_t ldw, int32_t m, int32_t n,
+                 int32_t k, const float* bias_dev, const float* residual_dev, int32_t ldr, void* out_dev, int32_t ldo,
+                 int32_t epilogue /* 0 bf16, 1 bf16+gelu, 2 f32, 3 f32+residual */, int32_t use_simt_reference,
+                 void* stream);
+int ec_gemm_argmax(const void* a_bf16_dev, int32_t lda, const void* w_bf16_dev, int32_t ldw, int32_t m, int32_t n,
+                   int32_t k, float* logits_dev /* nullable [m,n] */, int32_t* argmax_dev /* [m] */, void* ws_dev,
+                   size_t ws_bytes, void* stream);
+int ec_layernorm(const float* x_dev, int64_t ldx, const float* gamma_dev, const float* beta_dev, void* y_dev,
+                 int64_t ldy, int32_t y_is_bf16, int32_t rows, int32_t width, void* stream);
+int ec_attention(const void* q_dev, int64_t q_bs, int64_t q_rs, const void* k_dev, int64_t k_bs, int64_t k_rs,
+                 const void* v_dev, int64_t v_bs, int64_t v_rs, void* o_dev, int64_t o_bs, int64_t o_rs,
+                 int32_t batch, int32_t heads, int32_t sq, int32_t skv, int32_t head_dim, void* stream);
+int ec_check_watchdog(void* stream);   /* EC_ERR_TIMEOUT if a tcgen05 pipeline wait ever timed out */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EC_B200_H_ */

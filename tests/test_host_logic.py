@@ -1,0 +1,83 @@
+"""CPU: host-side logic of the shims (integer box policies, keys, sharding, tokenizer rendering, API surface)."""
+import numpy as np
+import pytest
+import torch
+
+from embodied_captioning_b200 import disagreement as dis
+from embodied_captioning_b200 import distributed as D
+from embodied_captioning_b200.captioner import transform as tr
+from embodied_captioning_b200.captioner.tokenizer import SimpleTokenizer
+from embodied_captioning_b200.config import get_config, list_models
+from oracle import preprocess_oracle as po
+
+
+@pytest.mark.parametrize("policy", [tr.POLICY_AGENT, tr.POLICY_PSEUDOLABELER, tr.POLICY_EVAL, tr.POLICY_PSEUDOCAPTIONER])
+@pytest.mark.parametrize("hw", [(480, 640), (1280, 1280)])
+def test_box_rects_bit_exact_vs_reference_restatement(policy, hw):
+    h, w = hw
+    rng = np.random.default_rng(policy * 7 + h)
+    x1 = rng.uniform(0, w - 2, 500); y1 = rng.uniform(0, h - 2, 500)
+    boxes = np.stack([x1, y1, np.minimum(x1 + rng.uniform(1, 400, 500), w), np.minimum(y1 + rng.uniform(1, 400, 500), h)], 1)
+    boxes = boxes.astype(np.float32)
+    if policy == tr.POLICY_EVAL:
+        boxes = np.trunc(boxes)
+    rects, flags = tr.box_rects(boxes, h, w, policy)
+    for i in range(len(boxes)):
+        r, pad, swap = po.crop_rect(policy, boxes[i], h, w)
+        assert rects[i].tolist() == r, (i, boxes[i])
+        assert bool(flags[i] & 1) == swap
+
+
+def test_keys_roundtrip_and_pandas_order():
+    k = dis.make_keys([10, 9, 10, 2], [1, 5, 11, 3])
+    e, o = dis.split_keys(k)
+    assert e.tolist() == [10, 9, 10, 2] and o.tolist() == [1, 5, 11, 3]
+    sk = np.sort(k)
+    order = dis.pandas_group_order(sk)
+    got = [(str(int(a)), str(int(b))) for a, b in zip(*dis.split_keys(sk[order]))]
+    assert got == [("10", "1"), ("10", "11"), ("2", "3"), ("9", "5")]
+    with pytest.raises(ValueError):
+        dis.make_keys([-1], [0])
+
+
+def test_shard_ranges_cover_everything():
+    for n in (0, 1, 7, 64, 1000):
+        for world in (1, 2, 4, 8):
+            spans = [D.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(e - s for s, e in spans) - min(e - s for s, e in spans) <= 1
+            assert max(e - s for s, e in spans) <= max(D.rows_per_rank(n, world), 0) or n == 0
+
+
+def test_pad_local_marks_padding():
+    emb = torch.randn(3, 8)
+    keys = torch.tensor([4, 5, 4])
+    pe, pk = D.pad_local(emb, keys, 5)
+    assert pe.shape == (5, 8) and pk.tolist()[3:] == [D.PAD_KEY, D.PAD_KEY]
+    assert torch.equal(pe[:3], emb) and float(pe[3:].norm(dim=1).min()) == 1.0
+
+
+def test_tokenizer_symbolic_fallback_keeps_string_protocol():
+    tok = SimpleTokenizer(vocab_size=49408)
+    s = tok.decode([49406, 320, 1125, 49407, 0, 0])
+    text = s.split("<end_of_text>")[0].replace("<start_of_text>", "")      # coca.py:30
+    if not tok.has_vocab:
+        assert text == "<tok_320> <tok_1125> "
+
+
+def test_model_registry():
+    assert "coca_ViT-L-14" in list_models() and "coca_ViT-B-32" in list_models()
+    c = get_config("coca_ViT-L-14")
+    assert (c.vision_width, c.vision_layers, c.patch_size, c.embed_dim, c.text_heads) == (1024, 24, 14, 768, 12)
+    assert c.vision_tokens == 257 and c.n_image_embs == 255
+    with pytest.raises(RuntimeError):
+        get_config("coca_ViT-H-14")
+
+
+def test_select_captioner_rejects_unknown_arch():
+    from embodied_captioning_b200.captioner.utils.utils import Configuration
+    from embodied_captioning_b200.captioner.utils.utils_captioner import select_captioner
+    cfg = Configuration(arch_name="florence", model_name="x", checkpoint_name=None, height=224, width=224)
+    with pytest.raises(AssertionError):
+        select_captioner(cfg.captioner)
