@@ -23,6 +23,7 @@ EXPORTS = [
     "ec_encode_image", "ec_decode_workspace_bytes", "ec_decode_greedy", "ec_forward_logits",
     "ec_disagreement_workspace_bytes", "ec_instance_disagreement", "ec_instance_disagreement_peers",
     "ec_gemm_bf16", "ec_gemm_argmax", "ec_layernorm", "ec_attention", "ec_check_watchdog",
+    "ec_launch_count", "ec_profile_gemm", "ec_profile_gemm_read",
 ]
 
 
@@ -79,10 +80,12 @@ def lib() -> C.CDLL:
     L.ec_layernorm.argtypes = [vp, i64, vp, vp, vp, i64, i32, i32, i32, vp]
     L.ec_attention.argtypes = [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64, i32, i32, i32, i32, i32, vp]
     L.ec_check_watchdog.argtypes = [vp]
+    L.ec_launch_count.argtypes = []
+    L.ec_launch_count.restype = C.c_int64
+    L.ec_profile_gemm.argtypes = [i32]
+    L.ec_profile_gemm_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     for name in EXPORTS:
-        fn = getattr(L, name)
-        if fn.restype is C.c_int and name not in ("ec_abi_version",):
-            fn.restype = C.c_int
+        getattr(L, name)          # AttributeError here means the .so is older than the header: rebuild
     _lib = L
     return L
 

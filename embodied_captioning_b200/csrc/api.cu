@@ -164,7 +164,7 @@ int ec_gemm_argmax(const void* a, int32_t lda, const void* w, int32_t ldw, int32
   g.n_parts = parts; g.eos_col = -1; g.min_len = 0;
   EC_TRY(gemm_bf16(g, EPI_ARGMAX, as_stream(stream)));
   argmax_parts_kernel<<<ceil_div(m, 128), 128, 0, as_stream(stream)>>>(g.part_val, g.part_idx, parts, m, argmax);
-  EC_CHECK_CUDA(cudaGetLastError());
+  EC_POST_LAUNCH();
   return EC_OK;
 }
 
@@ -189,5 +189,19 @@ int ec_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64
 }
 
 int ec_check_watchdog(void* stream) { return gemm_check_watchdog(as_stream(stream)); }
+
+int64_t ec_launch_count(void) { return (int64_t)launch_count(); }
+
+int ec_profile_gemm(int32_t enable) {
+  gemm_profile_enable(enable != 0);
+  return EC_OK;
+}
+
+int ec_profile_gemm_read(double* ms, double* flops, int64_t* launches) {
+  long long l = 0;
+  EC_TRY(gemm_profile_read(ms, flops, &l));
+  if (launches) *launches = l;
+  return EC_OK;
+}
 
 }  // extern "C"

@@ -173,7 +173,7 @@ static int launch_attn(const AttnArgs& a, cudaStream_t stream) {
   }
   dim3 grid(a.batch, a.heads);
   attention_full_kernel<D><<<grid, kAttnThreads, smem, stream>>>(a, skv_pad);
-  EC_CHECK_CUDA(cudaGetLastError());
+  EC_POST_LAUNCH();
   return EC_OK;
 }
 

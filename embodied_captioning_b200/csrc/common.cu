@@ -1,5 +1,6 @@
 #include "common.cuh"
 #include <cstring>
+#include <atomic>
 
 namespace ec {
 
@@ -13,6 +14,10 @@ void set_error(const char* fmt, ...) {
 }
 
 const char* last_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void note_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int num_sms() {
   static int cached[64] = {0};

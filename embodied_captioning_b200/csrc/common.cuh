@@ -40,6 +40,16 @@ const char* last_error();
 
 int num_sms();
 
+// kernel-launch accounting (bench.py reports how many of our kernels ran inside the timed region)
+void note_launches(long long n);
+long long launch_count();
+
+#define EC_POST_LAUNCH()                       \
+  do {                                         \
+    ::ec::note_launches(1);                    \
+    EC_CHECK_CUDA(cudaGetLastError());         \
+  } while (0)
+
 // ----------------------------------------------------------------------------- device helpers
 typedef __nv_bfloat16 bf16;
 

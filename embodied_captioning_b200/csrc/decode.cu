@@ -31,7 +31,7 @@ int decode_embed(const int* tokens, int ld_tokens, const float* tok_emb, const f
   const long long total = (long long)batch * (width / 4);
   const int grid = (int)std::min<long long>(ceil_div<long long>(total, 256), (long long)num_sms() * 8);
   decode_embed_kernel<<<grid, 256, 0, stream>>>(tokens, ld_tokens, tok_emb, pos_emb, x, batch, width, st);
-  EC_CHECK_CUDA(cudaGetLastError());
+  EC_POST_LAUNCH();
   return EC_OK;
 }
 
@@ -113,7 +113,7 @@ int decode_self_attention(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out
   EC_REQUIRE(head_dim == 64, EC_ERR_UNSUPPORTED, "decode self-attention: head_dim %d != 64", head_dim);
   const int grid = ceil_div(batch * heads, 4);
   decode_self_attn_kernel<64><<<grid, 128, 0, stream>>>(qkv, kcache, vcache, out, batch, heads, max_len, finished, st);
-  EC_CHECK_CUDA(cudaGetLastError());
+  EC_POST_LAUNCH();
   return EC_OK;
 }
 
@@ -221,7 +221,7 @@ int decode_cross_attention(const bf16* q, const bf16* kv, bf16* out, int batch, 
   EC_REQUIRE(n_kv <= 260, EC_ERR_UNSUPPORTED, "decode cross-attention: %d keys > 260", n_kv);
   const int grid = ceil_div(batch * heads, 4);
   decode_cross_attn_kernel<64><<<grid, 128, 0, stream>>>(q, kv, out, batch, heads, n_kv, finished, st);
-  EC_CHECK_CUDA(cudaGetLastError());
+  EC_POST_LAUNCH();
   return EC_OK;
 }
 
@@ -266,7 +266,7 @@ int decode_select(const float* part_val, const int* part_idx, int n_parts, int* 
                   cudaStream_t stream) {
   decode_select_kernel<<<ceil_div(batch, 8), 256, 0, stream>>>(part_val, part_idx, n_parts, tokens, ld_tokens, finished,
                                                               batch, seq_len, eos, pad, st);
-  EC_CHECK_CUDA(cudaGetLastError());
+  EC_POST_LAUNCH();
   return EC_OK;
 }
 
@@ -281,7 +281,7 @@ __global__ void decode_advance_kernel(DecodeState* st, int teacher_forced, int b
 
 int decode_advance(DecodeState* st, bool teacher_forced, int batch, cudaStream_t stream) {
   decode_advance_kernel<<<1, 1, 0, stream>>>(st, teacher_forced ? 1 : 0, batch);
-  EC_CHECK_CUDA(cudaGetLastError());
+  EC_POST_LAUNCH();
   return EC_OK;
 }
 
@@ -308,7 +308,7 @@ int decode_init(int* tokens, int ld_tokens, unsigned char* finished, int batch, 
   const long long total = (long long)batch * seq_len;
   const int grid = (int)std::min<long long>(ceil_div<long long>(total, 256), 1024);
   decode_init_kernel<<<grid, 256, 0, stream>>>(tokens, ld_tokens, finished, batch, seq_len, sot, pad, st);
-  EC_CHECK_CUDA(cudaGetLastError());
+  EC_POST_LAUNCH();
   return EC_OK;
 }
 

@@ -221,7 +221,7 @@ static int run(const float* emb, const float* const* peers_dev, int rows_per_ran
   const int grid = std::min(n, num_sms() * 4);
   segment_reduce_kernel<<<grid, kSegThreads, 0, stream>>>(emb, peers_dev, rows_per_rank, ld_emb, sidx, seg_start, out_m,
                                                           d, mode, part_rank, part_world, out_score, out_count);
-  EC_CHECK_CUDA(cudaGetLastError());
+  EC_POST_LAUNCH();
   return EC_OK;
 }
 

@@ -441,7 +441,7 @@ static int launch_tile(const GemmArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   gemm_tcgen05_kernel<BN, EPI><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tw, p, a.K, tiles_m, tiles_n);
-  EC_CHECK_CUDA(cudaGetLastError());
+  EC_POST_LAUNCH();
   return EC_OK;
 }
 
@@ -458,10 +458,56 @@ static int launch_epi(const GemmArgs& a, cudaStream_t stream) {
   }
 }
 
+// ---- optional per-launch timing (CUDA events on the launching stream) for the roofline line of bench.py
+struct ProfSlot { cudaEvent_t beg, end; double flops; };
+static bool g_prof_on = false;
+static std::vector<ProfSlot> g_prof_slots;
+static size_t g_prof_used = 0;
+
+void gemm_profile_enable(bool on) { g_prof_on = on; g_prof_used = 0; }
+
+int gemm_profile_read(double* ms, double* flops, long long* launches) {
+  double tms = 0.0, tf = 0.0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    EC_CHECK_CUDA(cudaEventSynchronize(g_prof_slots[i].end));
+    float t = 0.f;
+    EC_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof_slots[i].beg, g_prof_slots[i].end));
+    tms += t;
+    tf += g_prof_slots[i].flops;
+  }
+  if (ms) *ms = tms;
+  if (flops) *flops = tf;
+  if (launches) *launches = (long long)g_prof_used;
+  g_prof_used = 0;
+  return EC_OK;
+}
+
+static int gemm_dispatch(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream);
+
 int gemm_bf16(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream) {
+  if (!g_prof_on) return gemm_dispatch(a, epi, stream);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
+    return gemm_dispatch(a, epi, stream);
+  if (g_prof_used == g_prof_slots.size()) {
+    ProfSlot s{};
+    EC_CHECK_CUDA(cudaEventCreate(&s.beg));
+    EC_CHECK_CUDA(cudaEventCreate(&s.end));
+    g_prof_slots.push_back(s);
+  }
+  ProfSlot& s = g_prof_slots[g_prof_used];
+  EC_CHECK_CUDA(cudaEventRecord(s.beg, stream));
+  const int rc = gemm_dispatch(a, epi, stream);
+  EC_CHECK_CUDA(cudaEventRecord(s.end, stream));
+  if (rc == EC_OK) { s.flops = 2.0 * a.M * (double)a.N * a.K; ++g_prof_used; }
+  return rc;
+}
+
+static int gemm_dispatch(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream) {
   EC_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, EC_ERR_INVALID, "GEMM with empty dimension M=%d N=%d K=%d", a.M, a.N, a.K);
-  EC_REQUIRE(a.N % 8 == 0 && a.K % 8 == 0, EC_ERR_UNSUPPORTED, "GEMM needs N and K multiples of 8 (N=%d K=%d)", a.N,
-             a.K);
+  // K may be ragged (TMA zero-fills the box beyond K); only row strides need 16-byte alignment
+  EC_REQUIRE(a.N % 8 == 0, EC_ERR_UNSUPPORTED, "GEMM needs N to be a multiple of 8 (N=%d)", a.N);
+  EC_REQUIRE(a.lda >= a.K && a.ldw >= a.K, EC_ERR_INVALID, "GEMM row strides shorter than K");
   EC_REQUIRE(a.A && a.W, EC_ERR_INVALID, "GEMM null operand");
   if (epi != EPI_ARGMAX) {
     EC_REQUIRE(a.out != nullptr && a.ldo % 8 == 0, EC_ERR_INVALID, "GEMM output null or ldo %% 8 != 0");
@@ -524,7 +570,7 @@ int gemm_reference_simt(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream
   p.n_parts = a.n_parts; p.eos_col = a.eos_col; p.cur_len = a.cur_len; p.min_len = a.min_len; p.skip_flag = nullptr;
   dim3 grid(ceil_div(a.N, 128), a.M);
   gemm_simt_kernel<<<grid, 128, 0, stream>>>(a.A, a.lda, a.W, a.ldw, a.M, a.N, a.K, p, (int)epi);
-  EC_CHECK_CUDA(cudaGetLastError());
+  EC_POST_LAUNCH();
   return EC_OK;
 }
 

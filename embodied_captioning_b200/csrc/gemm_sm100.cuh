@@ -45,6 +45,10 @@ int gemm_bf16(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream);
 // cross-check the tensor-core kernel on device; never called by the model path).
 int gemm_reference_simt(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream);
 
+// per-launch CUDA-event timing of every non-captured gemm_bf16() call (bench.py roofline line)
+void gemm_profile_enable(bool on);
+int gemm_profile_read(double* ms, double* flops, long long* launches);
+
 // device-side watchdog flag (0 = fine). Reading it synchronises the stream.
 int gemm_check_watchdog(cudaStream_t stream);
 

@@ -86,7 +86,7 @@ int layernorm(const float* x, long long ldx, const float* gamma, const float* be
     layernorm_kernel<true><<<grid, wpb * 32, 0, stream>>>(x, ldx, gamma, beta, y, ldy, rows, width, skip_flag);
   else
     layernorm_kernel<false><<<grid, wpb * 32, 0, stream>>>(x, ldx, gamma, beta, y, ldy, rows, width, skip_flag);
-  EC_CHECK_CUDA(cudaGetLastError());
+  EC_POST_LAUNCH();
   return EC_OK;
 }
 
@@ -130,7 +130,7 @@ int vision_embed_ln_pre(const float* patch_emb, const float* cls, const float* p
   const int wpb = 8;
   vision_embed_ln_pre_kernel<<<(unsigned)ceil_div<long long>(rows, wpb), wpb * 32, 0, stream>>>(
       patch_emb, cls, pos, gamma, beta, out, batch, tokens, width);
-  EC_CHECK_CUDA(cudaGetLastError());
+  EC_POST_LAUNCH();
   return EC_OK;
 }
 
@@ -159,7 +159,7 @@ int im2col_patches(const bf16* img, bf16* out, int n, int size, int patch, int l
   const long long total = (long long)n * (size / patch) * (size / patch) * 3 * patch * patch;
   const int grid = (int)std::min<long long>(ceil_div<long long>(total, 256), (long long)num_sms() * 16);
   im2col_kernel<<<grid, 256, 0, stream>>>(img, out, n, size, patch, ld);
-  EC_CHECK_CUDA(cudaGetLastError());
+  EC_POST_LAUNCH();
   return EC_OK;
 }
 
@@ -181,7 +181,7 @@ int l2_normalize_rows(const float* x, long long ldx, float* y, long long ldy, in
                       cudaStream_t stream) {
   if (rows <= 0) return EC_OK;
   l2norm_kernel<<<ceil_div(rows, 8), 256, 0, stream>>>(x, ldx, y, ldy, rows, width);
-  EC_CHECK_CUDA(cudaGetLastError());
+  EC_POST_LAUNCH();
   return EC_OK;
 }
 
@@ -202,7 +202,7 @@ int convert_rows_f32_to_bf16(const float* x, long long ldx, bf16* y, long long l
   const long long total = (long long)rows * width;
   const int grid = (int)std::min<long long>(ceil_div<long long>(total, 256), (long long)num_sms() * 16);
   cvt_rows_kernel<<<grid, 256, 0, stream>>>(x, ldx, y, ldy, rows, width);
-  EC_CHECK_CUDA(cudaGetLastError());
+  EC_POST_LAUNCH();
   return EC_OK;
 }
 

@@ -337,7 +337,7 @@ int Model::encode_image(const bf16* x, int n, float* latent, float* embs, void* 
     const long long rows = (long long)n * Q;
     ln_post_split_kernel<<<(unsigned)ceil_div<long long>(rows, 8), 256, 0, s>>>(w.pool_out, ln_post_g, ln_post_b,
                                                                                w.pooled_bf16, embs, n, Q, E);
-    EC_CHECK_CUDA(cudaGetLastError());
+    EC_POST_LAUNCH();
   }
   if (latent != nullptr) {
     EC_TRY(linear(w.pooled_bf16, E, w_vproj, E, nullptr, n, E, E, w.pooled_proj, E, EPI_F32, nullptr, 0, nullptr, s));
@@ -472,7 +472,10 @@ int Model::run_steps(const DecodeWs& w, int* tokens, int ld_tokens, int n, int s
     if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
     cudaGraph_t graph = nullptr;
     EC_CHECK_CUDA(cudaStreamBeginCapture(side_stream, cudaStreamCaptureModeThreadLocal));
+    const long long before = launch_count();
     int rc = decode_step(w, tokens, ld_tokens, n, seq_len, min_len, logits, teacher_forced, side_stream);
+    graph_nodes = launch_count() - before;
+    note_launches(-graph_nodes);                      // captured, not launched
     cudaError_t ce = cudaStreamEndCapture(side_stream, &graph);
     if (rc != EC_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     EC_CHECK_CUDA(ce);
@@ -484,6 +487,7 @@ int Model::run_steps(const DecodeWs& w, int* tokens, int ld_tokens, int n, int s
   EC_CHECK_CUDA(cudaEventRecord(ev_in, s));
   EC_CHECK_CUDA(cudaStreamWaitEvent(side_stream, ev_in, 0));
   for (int t = 0; t < steps; ++t) EC_CHECK_CUDA(cudaGraphLaunch(graph_exec, side_stream));
+  note_launches(graph_nodes * steps);
   EC_CHECK_CUDA(cudaEventRecord(ev_out, side_stream));
   EC_CHECK_CUDA(cudaStreamWaitEvent(s, ev_out, 0));
   return EC_OK;

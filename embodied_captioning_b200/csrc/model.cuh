@@ -47,6 +47,7 @@ struct Model {
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   GraphKey graph_key{};
+  long long graph_nodes = 0;
 
   Model(const ec_config& c, int dev);
   ~Model();

@@ -229,7 +229,7 @@ int preprocess_crops(const unsigned char* frames, int n_frames, int frame_h, int
   a.out_bf16 = out_bf16; a.out_f32 = out_f32; a.status = status; a.max_strip_rows = max_strip_rows;
   dim3 grid(size / kBandRows, n);
   preprocess_kernel<<<grid, kPreThreads, smem, stream>>>(a);
-  EC_CHECK_CUDA(cudaGetLastError());
+  EC_POST_LAUNCH();
   return EC_OK;
 }
 

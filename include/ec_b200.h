@@ -115,6 +115,11 @@ int ec_attention(const void* q_dev, int64_t q_bs, int64_t q_rs, const void* k_de
                  int32_t batch, int32_t heads, int32_t sq, int32_t skv, int32_t head_dim, void* stream);
 int ec_check_watchdog(void* stream);   /* EC_ERR_TIMEOUT if a tcgen05 pipeline wait ever timed out */
 
+/* ---- measurement hooks used by bench.py */
+int64_t ec_launch_count(void);          /* kernels launched by this library so far (graph replays included) */
+int ec_profile_gemm(int32_t enable);    /* time every non-captured tcgen05 GEMM launch with CUDA events */
+int ec_profile_gemm_read(double* ms, double* flops, int64_t* launches);   /* sums since the last read; resets */
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,126 @@
+"""GPU: building-block kernels through the C ABI vs plain PyTorch fp32 references of the same op."""
+import pytest
+import torch
+
+from embodied_captioning_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_bf16(shape, dev, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).to(dev)
+
+
+GEMM_SHAPES = [
+    (128, 256, 64), (128, 256, 128), (256, 512, 1024), (257, 384, 128), (1000, 3072, 1024), (4, 768, 768),
+    (50, 128, 3072), (1024, 768, 3072), (300, 1536, 768), (130, 64, 64), (513, 1000, 592), (2570, 1024, 4096),
+    (3855, 3072, 1024),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_bf16_epilogues(device, M, N, K):
+    a = _rand_bf16((M, K), device, seed=1)
+    w = _rand_bf16((N, K), device, K ** -0.5, seed=2)
+    bias = torch.randn(N, device=device)
+    res = torch.randn(M, N, device=device)
+    ref = a.float() @ w.float().t() + bias
+    out = ops.gemm(a, w, bias, ops.EPI_BF16)
+    ops.check_watchdog(device)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 0.05, f"bf16 epilogue max err {err}"
+    assert torch.equal(out, ref.to(torch.bfloat16)) or (out.float() - ref).abs().max().item() < 0.05
+    out2 = ops.gemm(a, w, bias, ops.EPI_F32)
+    assert (out2 - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    out3 = ops.gemm(a, w, bias, ops.EPI_F32_RESID, residual=res)
+    assert (out3 - (ref + res)).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    out4 = ops.gemm(a, w, bias, ops.EPI_BF16_GELU)
+    assert (out4.float() - torch.nn.functional.gelu(ref)).abs().max().item() < 0.05
+    out5 = ops.gemm(a, w, None, ops.EPI_F32)
+    assert (out5 - (ref - bias)).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    ops.check_watchdog(device)
+
+
+def test_gemm_matches_simt_crosscheck(device):
+    a = _rand_bf16((300, 592), device, seed=3)
+    w = _rand_bf16((1024, 592), device, 0.05, seed=4)
+    t = ops.gemm(a[:, :588].contiguous() if False else a, w, None, ops.EPI_F32)
+    s = ops.gemm(a, w, None, ops.EPI_F32, simt_reference=True)
+    assert (t - s).abs().max().item() < 1e-3
+
+
+def test_gemm_k_tail_reads_zero_beyond_k(device):
+    """K = 588 inside rows of 592 elements (the ViT-L/14 patch GEMM): the TMA box over-reads columns 588..639,
+    which must come back as zeros although the padding columns hold garbage."""
+    a = _rand_bf16((257, 592), device, seed=5)
+    w = _rand_bf16((256, 592), device, 0.05, seed=6)
+    a[:, 588:] = 1000.0
+    w[:, 588:] = 1000.0
+    from embodied_captioning_b200 import _native as nat
+    out = torch.empty((257, 256), device=device, dtype=torch.float32)
+    nat.check(nat.lib().ec_gemm_bf16(a.data_ptr(), 592, w.data_ptr(), 592, 257, 256, 588, None, None, 0, out.data_ptr(),
+                                     256, ops.EPI_F32, 0, torch.cuda.current_stream().cuda_stream))
+    ref = a[:, :588].float() @ w[:, :588].float().t()
+    assert (out - ref).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 1024, 256), (1024, 49408, 768), (7, 2048, 512)])
+def test_gemm_argmax(device, M, N, K):
+    a = _rand_bf16((M, K), device, seed=7)
+    w = _rand_bf16((N, K), device, K ** -0.5, seed=8)
+    arg, logits = ops.gemm_argmax(a, w)
+    ops.check_watchdog(device)
+    ref = a.float() @ w.float().t()
+    assert (logits - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    assert torch.equal(arg.long(), logits.argmax(dim=-1))
+    top2 = ref.topk(2, dim=-1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-3
+    assert torch.equal(arg.long()[clear], ref.argmax(dim=-1)[clear])
+
+
+@pytest.mark.parametrize("rows,width", [(1, 128), (257, 1024), (1000, 768), (33, 512), (5, 256)])
+def test_layernorm(device, rows, width):
+    x = torch.randn(rows, width, device=device) * 3 + 1
+    g = torch.randn(width, device=device)
+    b = torch.randn(width, device=device)
+    ref = torch.nn.functional.layer_norm(x, (width,), g, b, 1e-5)
+    y32 = ops.layernorm(x, g, b, out_bf16=False)
+    assert (y32 - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    y16 = ops.layernorm(x, g, b, out_bf16=True)
+    assert torch.equal(y16, y32.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("B,H,Sq,Skv,D", [(3, 16, 257, 257, 64), (2, 12, 50, 50, 64), (2, 8, 256, 257, 96),
+                                          (2, 8, 256, 50, 64), (1, 8, 256, 50, 32), (5, 2, 50, 50, 64),
+                                          (1, 1, 1, 1, 64), (2, 4, 17, 33, 64)])
+def test_attention_full(device, B, H, Sq, Skv, D):
+    C = H * D
+    q = _rand_bf16((B, Sq, C), device, seed=11)
+    k = _rand_bf16((B, Skv, C), device, seed=12)
+    v = _rand_bf16((B, Skv, C), device, seed=13)
+    out = ops.attention(q, k, v, H)
+    qf = q.float().view(B, Sq, H, D).transpose(1, 2)
+    kf = k.float().view(B, Skv, H, D).transpose(1, 2)
+    vf = v.float().view(B, Skv, H, D).transpose(1, 2)
+    p = torch.softmax(qf @ kf.transpose(-1, -2) / D ** 0.5, dim=-1)
+    ref = (p @ vf).transpose(1, 2).reshape(B, Sq, C)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 0.03, f"attention max err {err}"
+    rel = ((out.float() - ref).norm() / ref.norm()).item()
+    assert rel < 1e-2, f"attention rel err {rel}"
+
+
+def test_attention_strided_fused_qkv_and_shared_queries(device):
+    """The two layouts the image tower uses: q/k/v as column slices of one [B,S,3C] buffer, and batch-shared
+    pooler queries."""
+    B, S, H, D = 2, 50, 4, 64
+    C = H * D
+    qkv = _rand_bf16((B, S, 3 * C), device, seed=21)
+    out = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H)
+    ref = ops.attention(qkv[:, :, :C].contiguous(), qkv[:, :, C:2 * C].contiguous(), qkv[:, :, 2 * C:].contiguous(), H)
+    assert torch.equal(out, ref)
+    q = _rand_bf16((16, C), device, seed=22)
+    out2 = ops.attention(q, qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H)
+    ref2 = ops.attention(q.unsqueeze(0).expand(B, -1, -1).contiguous(), qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H)
+    assert torch.equal(out2, ref2)
