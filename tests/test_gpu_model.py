@@ -110,13 +110,17 @@ def test_greedy_tokens_vs_oracle(tiny, device):
     out2 = model.generate(x.to(device), generation_type="top_k", seq_len=12)
     frac2, expl2 = _check_tokens(cfg, orc, embs_ref, out2["text"].cpu(), ref, 12)
     print(f"tiny end-to-end: identical sequences {frac2 * 100:.1f}% ({expl2} near-tie splits)")
-    # logits list protocol (ragged list, one entry per produced column)
+    # logits list protocol (ragged list, one entry per produced column); values compared on rows whose prefix
+    # still equals the oracle's (after a near-tie split the two models legitimately see different inputs)
+    got_tok, ref_tok = out["text"].cpu(), ref["text"]
     assert len(out["logits"]) == out["text"].shape[1] - 1
-    for lg_g, lg_r in zip(out["logits"], ref["logits"]):
+    for step, (lg_g, lg_r) in enumerate(zip(out["logits"], ref["logits"])):
         assert lg_g.shape == lg_r.shape
-        fin = torch.isfinite(lg_r)
-        assert torch.equal(torch.isfinite(lg_g.cpu()), fin)
-        assert ((lg_g.cpu()[fin] - lg_r[fin]).norm() / lg_r[fin].norm()).item() < 5e-2
+        same_prefix = (got_tok[:, :step + 1] == ref_tok[:, :step + 1]).all(dim=1)
+        g, r = lg_g.cpu()[same_prefix], lg_r[same_prefix]
+        fin = torch.isfinite(r)
+        assert torch.equal(torch.isfinite(g), fin)
+        assert ((g[fin] - r[fin]).norm() / r[fin].norm()).item() < 3e-2
 
 
 def test_cuda_graph_decode_is_identical(tiny, device):
