@@ -1,6 +1,7 @@
 #include "common.cuh"
 #include <cstring>
 #include <atomic>
+#include <cstdlib>
 
 namespace ec {
 
@@ -18,6 +19,15 @@ const char* last_error() { return g_err; }
 static std::atomic<long long> g_launches{0};
 void note_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EC_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 int num_sms() {
   static int cached[64] = {0};

@@ -50,6 +50,28 @@ long long launch_count();
     EC_CHECK_CUDA(cudaGetLastError());         \
   } while (0)
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the decoder step is launched with the programmatic-stream-serialization attribute: its
+// CTAs may be scheduled (and run their prologue) while the previous kernel drains; `pdl_wait()` then blocks
+// until the previous grid has completed and its writes are visible.  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();   // EC_PDL=0 disables (A/B testing)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                        cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ----------------------------------------------------------------------------- device helpers
 typedef __nv_bfloat16 bf16;
 

@@ -1,7 +1,8 @@
 // KV-cached greedy decoder step kernels (one new token per crop per step; memory-bound).
 // All kernels read the step index from a device-resident DecodeState so one captured CUDA graph serves
 // every step, and early-out when every crop has finished (no per-token host synchronisation, unlike the
-// reference loop at coca_model.py:294-327 which syncs on `mask.all()` each step).
+// reference loop at coca_model.py:294-327 which syncs on `mask.all()` each step).  Every kernel is launched
+// with programmatic dependent launch so launch latency and CTA scheduling overlap the previous kernel's tail.
 #include "kernels.cuh"
 
 namespace ec {
@@ -11,6 +12,8 @@ __global__ void __launch_bounds__(256) decode_embed_kernel(const int* __restrict
                                                            const float* __restrict__ tok_emb,
                                                            const float* __restrict__ pos_emb, float* __restrict__ x,
                                                            int batch, int width, const DecodeState* __restrict__ st) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (st->done) return;
   const int pos = st->cur_len - 1;
   const int nvec = width >> 2;
@@ -30,173 +33,68 @@ int decode_embed(const int* tokens, int ld_tokens, const float* tok_emb, const f
   EC_REQUIRE(width % 4 == 0, EC_ERR_UNSUPPORTED, "decode_embed: width %% 4 != 0");
   const long long total = (long long)batch * (width / 4);
   const int grid = (int)std::min<long long>(ceil_div<long long>(total, 256), (long long)num_sms() * 8);
-  decode_embed_kernel<<<grid, 256, 0, stream>>>(tokens, ld_tokens, tok_emb, pos_emb, x, batch, width, st);
-  EC_POST_LAUNCH();
+  note_launches(1);
+  EC_CHECK_CUDA(launch_kernel(decode_embed_kernel, dim3(grid), dim3(256), 0, stream, tokens, ld_tokens, tok_emb,
+                              pos_emb, x, batch, width, st));
   return EC_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Self-attention of the new token: one warp per (crop, head).  head_dim = 64: lane owns dims 2*lane, 2*lane+1.
-constexpr int kMaxCtx = 128;   // >= context_length + 1
+// Single-query attention over `n` cached keys for one (crop, head), executed by one warp.
+// Key j lives at kbase + j*rstride (64 bf16 = one 128-byte line), value at vbase + j*rstride.  8 lanes cover a
+// row (16 B each), 4 rows per warp instruction, 4 independent instructions (16 rows) in flight per lane.
+constexpr int kMaxKeys = 260;   // >= n_queries-1 and >= context_length+1
 
-template <int D>
-__global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kcache,
-                                                               bf16* __restrict__ vcache, bf16* __restrict__ out,
-                                                               int batch, int heads, int max_len,
-                                                               const unsigned char* __restrict__ finished,
-                                                               const DecodeState* __restrict__ st) {
-  if (st->done) return;
-  __shared__ float s_q[4][D];
-  __shared__ float s_p[4][kMaxCtx];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = blockIdx.x * 4 + w;
-  if (pair >= batch * heads) return;
-  const int b = pair / heads, h = pair % heads;
-  if (finished[b]) return;
-  const int pos = st->cur_len - 1;           // position of the new token; attends to 0..pos
-  const int C = heads * D;
-  const bf16* row = qkv + (size_t)b * 3 * C + h * D;
-  bf16* kc = kcache + ((size_t)b * max_len) * C + h * D;
-  bf16* vc = vcache + ((size_t)b * max_len) * C + h * D;
-  // append k, v of the new token; stash q (pre-scaled) in shared memory
-  const float scale = rsqrtf((float)D);
-  for (int d = lane; d < D; d += 32) {
-    s_q[w][d] = __bfloat162float(row[d]) * scale;
-    kc[(size_t)pos * C + d] = row[C + d];
-    vc[(size_t)pos * C + d] = row[2 * C + d];
-  }
-  __syncwarp();
-  // scores: lane j handles positions j, j+32, ...
+__device__ __forceinline__ void warp_attend(const float (&qf)[8], const bf16* kbase, const bf16* vbase, size_t rstride,
+                                            int n, float* s_p, int lane, float (&acc)[8], float& inv) {
+  const int grp = lane >> 3;
   float mx = -INFINITY;
-  for (int j = lane; j <= pos; j += 32) {
-    const uint4* kr = reinterpret_cast<const uint4*>(kc + (size_t)j * C);
-    float acc = 0.f;
-#pragma unroll
-    for (int c = 0; c < D / 8; ++c) {
-      const uint4 u = kr[c];
-      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-      const float* q = &s_q[w][c * 8];
-      acc += a0.x * q[0] + a0.y * q[1] + a1.x * q[2] + a1.y * q[3] + a2.x * q[4] + a2.y * q[5] + a3.x * q[6] + a3.y * q[7];
-    }
-    s_p[w][j] = acc;
-    mx = fmaxf(mx, acc);
-  }
-  mx = warp_max(mx);
-  float sum = 0.f;
-  for (int j = lane; j <= pos; j += 32) {
-    const float e = __expf(s_p[w][j] - mx);
-    s_p[w][j] = e;
-    sum += e;
-  }
-  sum = warp_sum(sum);
-  __syncwarp();
-  const float inv = 1.0f / sum;
-  // out[d] = sum_j p_j V[j][d]; each lane owns D/32 consecutive dims
-  constexpr int DPL = D / 32;
-  float acc[DPL];
-#pragma unroll
-  for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
-  for (int j = 0; j <= pos; ++j) {
-    const float p = s_p[w][j];
-    const bf16* vr = vc + (size_t)j * C + lane * DPL;
-#pragma unroll
-    for (int i = 0; i < DPL; ++i) acc[i] += p * __bfloat162float(vr[i]);
-  }
-  bf16* o = out + (size_t)b * C + h * D + lane * DPL;
-#pragma unroll
-  for (int i = 0; i < DPL; ++i) o[i] = __float2bfloat16_rn(acc[i] * inv);
-}
-
-int decode_self_attention(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, int batch, int heads, int head_dim,
-                          int max_len, const unsigned char* finished, const DecodeState* st, cudaStream_t stream) {
-  EC_REQUIRE(max_len <= kMaxCtx, EC_ERR_UNSUPPORTED, "decode: context %d > %d", max_len, kMaxCtx);
-  EC_REQUIRE(head_dim == 64, EC_ERR_UNSUPPORTED, "decode self-attention: head_dim %d != 64", head_dim);
-  const int grid = ceil_div(batch * heads, 4);
-  decode_self_attn_kernel<64><<<grid, 128, 0, stream>>>(qkv, kcache, vcache, out, batch, heads, max_len, finished, st);
-  EC_POST_LAUNCH();
-  return EC_OK;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Cross-attention over the image K/V cache: one warp per (crop, head).  The cache row of key j is
-// [K(C) | V(C)] bf16; head h owns a contiguous 128-byte segment of each half.  8 lanes cover one key row
-// (16 B each), 4 rows per warp instruction, 4 independent instructions in flight per lane.
-template <int D>
-__global__ void __launch_bounds__(128) decode_cross_attn_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kv,
-                                                                bf16* __restrict__ out, int batch, int heads, int n_kv,
-                                                                const unsigned char* __restrict__ finished,
-                                                                const DecodeState* __restrict__ st) {
-  static_assert(D == 64, "lane mapping assumes 64-dim heads");
-  if (st->done) return;
-  __shared__ float s_p[4][260];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = blockIdx.x * 4 + w;
-  if (pair >= batch * heads) return;
-  const int b = pair / heads, h = pair % heads;
-  if (finished[b]) return;
-  const int C = heads * D;
-  const int sub = lane & 7, grp = lane >> 3;           // 16-byte slice of the head, row within a group of 4
-  float qf[8];
-  {
-    const uint4 u = *reinterpret_cast<const uint4*>(q + (size_t)b * C + h * D + sub * 8);
-    const float sc = rsqrtf((float)D);
-    const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-    qf[0] = a0.x * sc; qf[1] = a0.y * sc; qf[2] = a1.x * sc; qf[3] = a1.y * sc;
-    qf[4] = a2.x * sc; qf[5] = a2.y * sc; qf[6] = a3.x * sc; qf[7] = a3.y * sc;
-  }
-  const bf16* kbase = kv + (size_t)b * n_kv * 2 * C + h * D + sub * 8;
-  const size_t rstride = (size_t)2 * C;
-  // ---- pass 1: scores
-  float mx = -INFINITY;
-  for (int j0 = 0; j0 < n_kv; j0 += 16) {
+  for (int j0 = 0; j0 < n; j0 += 16) {
     uint4 u[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int j = j0 + i * 4 + grp;
-      u[i] = (j < n_kv) ? __ldg(reinterpret_cast<const uint4*>(kbase + (size_t)j * rstride)) : make_uint4(0, 0, 0, 0);
+      u[i] = (j < n) ? *reinterpret_cast<const uint4*>(kbase + (size_t)j * rstride) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float2 a0 = unpack_bf16x2(u[i].x), a1 = unpack_bf16x2(u[i].y), a2 = unpack_bf16x2(u[i].z), a3 = unpack_bf16x2(u[i].w);
-      float acc = a0.x * qf[0] + a0.y * qf[1] + a1.x * qf[2] + a1.y * qf[3] + a2.x * qf[4] + a2.y * qf[5] +
-                  a3.x * qf[6] + a3.y * qf[7];
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      float d = a0.x * qf[0] + a0.y * qf[1] + a1.x * qf[2] + a1.y * qf[3] + a2.x * qf[4] + a2.y * qf[5] +
+                a3.x * qf[6] + a3.y * qf[7];
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
       const int j = j0 + i * 4 + grp;
-      if (j < n_kv) {
-        if (sub == 0) s_p[w][j] = acc;
-        mx = fmaxf(mx, acc);
+      if (j < n) {
+        if ((lane & 7) == 0) s_p[j] = d;
+        mx = fmaxf(mx, d);
       }
     }
   }
   mx = warp_max(mx);
   __syncwarp();
   float sum = 0.f;
-  for (int j = lane; j < n_kv; j += 32) {
-    const float e = __expf(s_p[w][j] - mx);
-    s_p[w][j] = e;
+  for (int j = lane; j < n; j += 32) {
+    const float e = __expf(s_p[j] - mx);
+    s_p[j] = e;
     sum += e;
   }
   sum = warp_sum(sum);
   __syncwarp();
-  const float inv = 1.0f / sum;
-  // ---- pass 2: weighted sum of V
-  float acc[8];
+  inv = 1.0f / sum;
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  const bf16* vbase = kbase + C;
-  for (int j0 = 0; j0 < n_kv; j0 += 16) {
+  for (int j0 = 0; j0 < n; j0 += 16) {
     uint4 u[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int j = j0 + i * 4 + grp;
-      u[i] = (j < n_kv) ? __ldg(reinterpret_cast<const uint4*>(vbase + (size_t)j * rstride)) : make_uint4(0, 0, 0, 0);
+      u[i] = (j < n) ? *reinterpret_cast<const uint4*>(vbase + (size_t)j * rstride) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int j = j0 + i * 4 + grp;
-      const float p = (j < n_kv) ? s_p[w][j] : 0.f;
+      const float p = (j < n) ? s_p[j] : 0.f;
       const float2 a0 = unpack_bf16x2(u[i].x), a1 = unpack_bf16x2(u[i].y), a2 = unpack_bf16x2(u[i].z), a3 = unpack_bf16x2(u[i].w);
       acc[0] += p * a0.x; acc[1] += p * a0.y; acc[2] += p * a1.x; acc[3] += p * a1.y;
       acc[4] += p * a2.x; acc[5] += p * a2.y; acc[6] += p * a3.x; acc[7] += p * a3.y;
@@ -207,21 +105,98 @@ __global__ void __launch_bounds__(128) decode_cross_attn_kernel(const bf16* __re
     acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
     acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
   }
-  if (grp == 0) {
-    uint4 o;
-    o.x = pack_bf16x2(acc[0] * inv, acc[1] * inv); o.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
-    o.z = pack_bf16x2(acc[4] * inv, acc[5] * inv); o.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
-    *reinterpret_cast<uint4*>(out + (size_t)b * C + h * D + sub * 8) = o;
-  }
+}
+
+__device__ __forceinline__ void load_q_slice(const bf16* q, float (&qf)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(q);
+  const float sc = 0.125f;   // 1/sqrt(64)
+  const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+  qf[0] = a0.x * sc; qf[1] = a0.y * sc; qf[2] = a1.x * sc; qf[3] = a1.y * sc;
+  qf[4] = a2.x * sc; qf[5] = a2.y * sc; qf[6] = a3.x * sc; qf[7] = a3.y * sc;
+}
+
+__device__ __forceinline__ void store_out_slice(bf16* o, const float (&acc)[8], float inv) {
+  uint4 v;
+  v.x = pack_bf16x2(acc[0] * inv, acc[1] * inv); v.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+  v.z = pack_bf16x2(acc[4] * inv, acc[5] * inv); v.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
+  *reinterpret_cast<uint4*>(o) = v;
+}
+
+// causal self-attention of the new token: appends its k, v to the cache, then attends to positions 0..pos
+__global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __restrict__ qkv, bf16* kcache, bf16* vcache,
+                                                               bf16* __restrict__ out, int batch, int heads, int max_len,
+                                                               const unsigned char* __restrict__ finished,
+                                                               const DecodeState* __restrict__ st) {
+  constexpr int D = 64;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (st->done) return;
+  __shared__ float s_p[4][kMaxKeys];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * 4 + w;
+  if (pair >= batch * heads) return;
+  const int b = pair / heads, h = pair % heads;
+  if (finished[b]) return;
+  const int pos = st->cur_len - 1;
+  const int C = heads * D;
+  const int sub = lane & 7, grp = lane >> 3;
+  const bf16* row = qkv + (size_t)b * 3 * C + h * D + sub * 8;
+  bf16* kc = kcache + ((size_t)b * max_len) * C + h * D + sub * 8;
+  bf16* vc = vcache + ((size_t)b * max_len) * C + h * D + sub * 8;
+  if (grp == 0) *reinterpret_cast<uint4*>(kc + (size_t)pos * C) = *reinterpret_cast<const uint4*>(row + C);
+  if (grp == 1) *reinterpret_cast<uint4*>(vc + (size_t)pos * C) = *reinterpret_cast<const uint4*>(row + 2 * C);
+  float qf[8];
+  load_q_slice(row, qf);
+  __syncwarp();     // the appended row is read back by other lanes of this warp below
+  float acc[8], inv;
+  warp_attend(qf, kc, vc, (size_t)C, pos + 1, s_p[w], lane, acc, inv);
+  if (grp == 0) store_out_slice(out + (size_t)b * C + h * D + sub * 8, acc, inv);
+}
+
+int decode_self_attention(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, int batch, int heads, int head_dim,
+                          int max_len, const unsigned char* finished, const DecodeState* st, cudaStream_t stream) {
+  EC_REQUIRE(max_len <= kMaxKeys, EC_ERR_UNSUPPORTED, "decode: context %d > %d", max_len, kMaxKeys);
+  EC_REQUIRE(head_dim == 64, EC_ERR_UNSUPPORTED, "decode self-attention: head_dim %d != 64", head_dim);
+  const int grid = ceil_div(batch * heads, 4);
+  note_launches(1);
+  EC_CHECK_CUDA(launch_kernel(decode_self_attn_kernel, dim3(grid), dim3(128), 0, stream, qkv, kcache, vcache, out, batch,
+                              heads, max_len, finished, st));
+  return EC_OK;
+}
+
+// cross-attention over the image K/V cache: the cache row of key j is [K(C) | V(C)] bf16
+__global__ void __launch_bounds__(128) decode_cross_attn_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kv,
+                                                                bf16* __restrict__ out, int batch, int heads, int n_kv,
+                                                                const unsigned char* __restrict__ finished,
+                                                                const DecodeState* __restrict__ st) {
+  constexpr int D = 64;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (st->done) return;
+  __shared__ float s_p[4][kMaxKeys];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * 4 + w;
+  if (pair >= batch * heads) return;
+  const int b = pair / heads, h = pair % heads;
+  if (finished[b]) return;
+  const int C = heads * D;
+  const int sub = lane & 7;
+  float qf[8];
+  load_q_slice(q + (size_t)b * C + h * D + sub * 8, qf);
+  const bf16* kbase = kv + (size_t)b * n_kv * 2 * C + h * D + sub * 8;
+  float acc[8], inv;
+  warp_attend(qf, kbase, kbase + C, (size_t)2 * C, n_kv, s_p[w], lane, acc, inv);
+  if ((lane >> 3) == 0) store_out_slice(out + (size_t)b * C + h * D + sub * 8, acc, inv);
 }
 
 int decode_cross_attention(const bf16* q, const bf16* kv, bf16* out, int batch, int heads, int head_dim, int n_kv,
                            const unsigned char* finished, const DecodeState* st, cudaStream_t stream) {
   EC_REQUIRE(head_dim == 64, EC_ERR_UNSUPPORTED, "decode cross-attention: head_dim %d != 64", head_dim);
-  EC_REQUIRE(n_kv <= 260, EC_ERR_UNSUPPORTED, "decode cross-attention: %d keys > 260", n_kv);
+  EC_REQUIRE(n_kv <= kMaxKeys, EC_ERR_UNSUPPORTED, "decode cross-attention: %d keys > %d", n_kv, kMaxKeys);
   const int grid = ceil_div(batch * heads, 4);
-  decode_cross_attn_kernel<64><<<grid, 128, 0, stream>>>(q, kv, out, batch, heads, n_kv, finished, st);
-  EC_POST_LAUNCH();
+  note_launches(1);
+  EC_CHECK_CUDA(launch_kernel(decode_cross_attn_kernel, dim3(grid), dim3(128), 0, stream, q, kv, out, batch, heads, n_kv,
+                              finished, st));
   return EC_OK;
 }
 
@@ -232,6 +207,8 @@ __global__ void __launch_bounds__(256) decode_select_kernel(const float* __restr
                                                             int* __restrict__ tokens, int ld_tokens,
                                                             unsigned char* __restrict__ finished, int batch,
                                                             int seq_len, int eos, int pad, DecodeState* st) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (st->done) return;
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -264,13 +241,15 @@ __global__ void __launch_bounds__(256) decode_select_kernel(const float* __restr
 int decode_select(const float* part_val, const int* part_idx, int n_parts, int* tokens, int ld_tokens,
                   unsigned char* finished, int batch, int seq_len, int eos, int pad, DecodeState* st,
                   cudaStream_t stream) {
-  decode_select_kernel<<<ceil_div(batch, 8), 256, 0, stream>>>(part_val, part_idx, n_parts, tokens, ld_tokens, finished,
-                                                              batch, seq_len, eos, pad, st);
-  EC_POST_LAUNCH();
+  note_launches(1);
+  EC_CHECK_CUDA(launch_kernel(decode_select_kernel, dim3(ceil_div(batch, 8)), dim3(256), 0, stream, part_val, part_idx,
+                              n_parts, tokens, ld_tokens, finished, batch, seq_len, eos, pad, st));
   return EC_OK;
 }
 
 __global__ void decode_advance_kernel(DecodeState* st, int teacher_forced, int batch) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (st->done) return;
   st->cur_len += 1;
   const int act = teacher_forced ? batch : st->next_active;   // teacher forcing never finishes a row
@@ -280,8 +259,8 @@ __global__ void decode_advance_kernel(DecodeState* st, int teacher_forced, int b
 }
 
 int decode_advance(DecodeState* st, bool teacher_forced, int batch, cudaStream_t stream) {
-  decode_advance_kernel<<<1, 1, 0, stream>>>(st, teacher_forced ? 1 : 0, batch);
-  EC_POST_LAUNCH();
+  note_launches(1);
+  EC_CHECK_CUDA(launch_kernel(decode_advance_kernel, dim3(1), dim3(1), 0, stream, st, teacher_forced ? 1 : 0, batch));
   return EC_OK;
 }
 

@@ -1,0 +1,224 @@
+// Host side of the tcgen05 GEMM: tensor maps, tile-shape heuristic, launch, profiling hooks, SIMT cross-check.
+#include "gemm_kernel.cuh"
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+#include <vector>
+
+namespace ec {
+
+// ============================================================================================
+// Host side: tensor maps + launch
+// ============================================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle
+static int make_tmap(CUtensorMap* out, const bf16* base, int rows, int cols, int ld, int box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  EC_REQUIRE(fn != nullptr, EC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  EC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0, EC_ERR_INVALID, "GEMM operand not 16-byte aligned");
+  EC_REQUIRE(ld % 8 == 0, EC_ERR_INVALID, "GEMM operand row stride %d not a multiple of 8 elements", ld);
+  // descriptors are pure functions of (base, shape, stride, box): memoise them, encoding costs microseconds
+  struct Key { const void* p; int r, c, l, b; };
+  struct Entry { Key k; CUtensorMap m; };
+  static std::mutex mu;
+  static std::vector<Entry> cache[256];
+  const size_t hsh = ((reinterpret_cast<uintptr_t>(base) >> 8) ^ (size_t)rows * 131u ^ (size_t)box_rows) & 255u;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    for (const Entry& e : cache[hsh])
+      if (e.k.p == base && e.k.r == rows && e.k.c == cols && e.k.l == ld && e.k.b == box_rows) {
+        *out = e.m;
+        return EC_OK;
+      }
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(bf16)};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EC_REQUIRE(r == CUDA_SUCCESS, EC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache[hsh].size() < 64) cache[hsh].push_back(Entry{Key{base, rows, cols, ld, box_rows}, *out});
+  }
+  return EC_OK;
+}
+
+int gemm_argmax_parts(int N) { return ceil_div(N, 256) * 2; }
+
+template <int BN, int EPI>
+static int launch_tile(const GemmArgs& a, cudaStream_t stream) {
+  using Cfg = TileCfg<BN>;
+  CUtensorMap ta, tw;
+  EC_TRY(make_tmap(&ta, a.A, a.M, a.K, a.lda, kBM));
+  EC_TRY(make_tmap(&tw, a.W, a.N, a.K, a.ldw, BN));
+  EpiParams p;
+  p.M = a.M; p.N = a.N; p.bias = a.bias; p.residual = a.residual; p.ldr = a.ldr; p.out = a.out; p.ldo = a.ldo;
+  p.logits = a.logits; p.ld_logits = a.ld_logits; p.logits_step_stride = a.logits_step_stride; p.part_val = a.part_val; p.part_idx = a.part_idx;
+  p.n_parts = a.n_parts; p.eos_col = a.eos_col; p.cur_len = a.cur_len; p.min_len = a.min_len;
+  p.skip_flag = a.skip_flag;
+  const int tiles_m = ceil_div(a.M, kBM), tiles_n = ceil_div(a.N, BN);
+  const int grid = std::min(tiles_m * tiles_n, num_sms());
+  static bool attr_set = false;   // per template instantiation
+  if (!attr_set) {
+    EC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  note_launches(1);
+  EC_CHECK_CUDA(launch_kernel(gemm_tcgen05_kernel<BN, EPI>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, stream,
+                              ta, tw, p, a.K, tiles_m, tiles_n));
+  return EC_OK;
+}
+
+template <int EPI>
+static int launch_epi(const GemmArgs& a, cudaStream_t stream) {
+  if constexpr (EPI == EPI_ARGMAX) {
+    return launch_tile<256, EPI>(a, stream);
+  } else {
+  static const int forced = [] { const char* e = getenv("EC_GEMM_BN"); return e ? atoi(e) : 0; }();
+  if (forced == 256) return launch_tile<256, EPI>(a, stream);
+  if (forced == 128) return launch_tile<128, EPI>(a, stream);
+  if (forced == 64) return launch_tile<64, EPI>(a, stream);
+  const int sms = num_sms();
+  const int tm = ceil_div(a.M, kBM);
+  if (tm * ceil_div(a.N, 256) >= sms) return launch_tile<256, EPI>(a, stream);
+  if (tm * ceil_div(a.N, 128) >= sms / 2 || a.N >= 1024) return launch_tile<128, EPI>(a, stream);
+  return launch_tile<64, EPI>(a, stream);
+  }
+}
+
+// ---- optional per-launch timing (CUDA events on the launching stream) for the roofline line of bench.py
+struct ProfSlot { cudaEvent_t beg, end; double flops; };
+static bool g_prof_on = false;
+static std::vector<ProfSlot> g_prof_slots;
+static size_t g_prof_used = 0;
+
+void gemm_profile_enable(bool on) { g_prof_on = on; g_prof_used = 0; }
+
+int gemm_profile_read(double* ms, double* flops, long long* launches) {
+  double tms = 0.0, tf = 0.0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    EC_CHECK_CUDA(cudaEventSynchronize(g_prof_slots[i].end));
+    float t = 0.f;
+    EC_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof_slots[i].beg, g_prof_slots[i].end));
+    tms += t;
+    tf += g_prof_slots[i].flops;
+  }
+  if (ms) *ms = tms;
+  if (flops) *flops = tf;
+  if (launches) *launches = (long long)g_prof_used;
+  g_prof_used = 0;
+  return EC_OK;
+}
+
+static int gemm_dispatch(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream);
+
+int gemm_bf16(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream) {
+  if (!g_prof_on) return gemm_dispatch(a, epi, stream);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
+    return gemm_dispatch(a, epi, stream);
+  if (g_prof_used == g_prof_slots.size()) {
+    ProfSlot s{};
+    EC_CHECK_CUDA(cudaEventCreate(&s.beg));
+    EC_CHECK_CUDA(cudaEventCreate(&s.end));
+    g_prof_slots.push_back(s);
+  }
+  ProfSlot& s = g_prof_slots[g_prof_used];
+  EC_CHECK_CUDA(cudaEventRecord(s.beg, stream));
+  const int rc = gemm_dispatch(a, epi, stream);
+  EC_CHECK_CUDA(cudaEventRecord(s.end, stream));
+  if (rc == EC_OK) { s.flops = 2.0 * a.M * (double)a.N * a.K; ++g_prof_used; }
+  return rc;
+}
+
+static int gemm_dispatch(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream) {
+  EC_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, EC_ERR_INVALID, "GEMM with empty dimension M=%d N=%d K=%d", a.M, a.N, a.K);
+  // K may be ragged (TMA zero-fills the box beyond K); only row strides need 16-byte alignment
+  EC_REQUIRE(a.N % 8 == 0, EC_ERR_UNSUPPORTED, "GEMM needs N to be a multiple of 8 (N=%d)", a.N);
+  EC_REQUIRE(a.lda >= a.K && a.ldw >= a.K, EC_ERR_INVALID, "GEMM row strides shorter than K");
+  EC_REQUIRE(a.A && a.W, EC_ERR_INVALID, "GEMM null operand");
+  if (epi != EPI_ARGMAX) {
+    EC_REQUIRE(a.out != nullptr && a.ldo % 8 == 0, EC_ERR_INVALID, "GEMM output null or ldo %% 8 != 0");
+    EC_REQUIRE((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0, EC_ERR_INVALID, "GEMM output not 16-byte aligned");
+  } else {
+    EC_REQUIRE(a.part_val && a.part_idx && a.n_parts == gemm_argmax_parts(a.N), EC_ERR_INVALID,
+               "arg-max GEMM needs part buffers with n_parts=%d", gemm_argmax_parts(a.N));
+    EC_REQUIRE(a.logits == nullptr || a.ld_logits % 4 == 0, EC_ERR_INVALID, "logits row stride must be a multiple of 4");
+  }
+  if (epi == EPI_F32_RESID)
+    EC_REQUIRE(a.residual != nullptr && a.ldr % 4 == 0, EC_ERR_INVALID, "residual epilogue needs a residual pointer");
+  if (a.bias) EC_REQUIRE((reinterpret_cast<uintptr_t>(a.bias) & 15u) == 0, EC_ERR_INVALID, "bias not 16-byte aligned");
+  switch (epi) {
+    case EPI_BF16: return launch_epi<EPI_BF16>(a, stream);
+    case EPI_BF16_GELU: return launch_epi<EPI_BF16_GELU>(a, stream);
+    case EPI_F32: return launch_epi<EPI_F32>(a, stream);
+    case EPI_F32_RESID: return launch_epi<EPI_F32_RESID>(a, stream);
+    case EPI_ARGMAX: return launch_epi<EPI_ARGMAX>(a, stream);
+  }
+  set_error("unknown GEMM epilogue %d", (int)epi);
+  return EC_ERR_INVALID;
+}
+
+int gemm_check_watchdog(cudaStream_t stream) {
+  EC_CHECK_CUDA(cudaStreamSynchronize(stream));
+  int v = 0;
+  EC_CHECK_CUDA(cudaMemcpyFromSymbol(&v, g_gemm_watchdog, sizeof(int)));
+  if (v != 0) {
+    int zero = 0;
+    cudaMemcpyToSymbol(g_gemm_watchdog, &zero, sizeof(int));
+    set_error("tcgen05 GEMM pipeline wait timed out (role code %d)", v);
+    return EC_ERR_TIMEOUT;
+  }
+  return EC_OK;
+}
+
+// ============================================================================================
+// SIMT cross-check kernel (tests only)
+// ============================================================================================
+__global__ void gemm_simt_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W, int ldw, int M, int N,
+                                 int K, EpiParams p, int epi) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;
+  if (col >= N || row >= M) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc += __bfloat162float(A[(size_t)row * lda + k]) * __bfloat162float(W[(size_t)col * ldw + k]);
+  if (p.bias) acc += p.bias[col];
+  if (epi == EPI_BF16) reinterpret_cast<bf16*>(p.out)[(size_t)row * p.ldo + col] = __float2bfloat16_rn(acc);
+  else if (epi == EPI_BF16_GELU) reinterpret_cast<bf16*>(p.out)[(size_t)row * p.ldo + col] = __float2bfloat16_rn(gelu_erf(acc));
+  else if (epi == EPI_F32) reinterpret_cast<float*>(p.out)[(size_t)row * p.ldo + col] = acc;
+  else if (epi == EPI_F32_RESID)
+    reinterpret_cast<float*>(p.out)[(size_t)row * p.ldo + col] = acc + p.residual[(size_t)row * p.ldr + col];
+  else if (p.logits) p.logits[(size_t)row * p.ld_logits + col] = acc;
+}
+
+int gemm_reference_simt(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream) {
+  EpiParams p;
+  p.M = a.M; p.N = a.N; p.bias = a.bias; p.residual = a.residual; p.ldr = a.ldr; p.out = a.out; p.ldo = a.ldo;
+  p.logits = a.logits; p.ld_logits = a.ld_logits; p.logits_step_stride = a.logits_step_stride; p.part_val = a.part_val; p.part_idx = a.part_idx;
+  p.n_parts = a.n_parts; p.eos_col = a.eos_col; p.cur_len = a.cur_len; p.min_len = a.min_len; p.skip_flag = nullptr;
+  dim3 grid(ceil_div(a.N, 128), a.M);
+  gemm_simt_kernel<<<grid, 128, 0, stream>>>(a.A, a.lda, a.W, a.ldw, a.M, a.N, a.K, p, (int)epi);
+  EC_POST_LAUNCH();
+  return EC_OK;
+}
+
+}  // namespace ec

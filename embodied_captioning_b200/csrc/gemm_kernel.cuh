@@ -1,15 +1,17 @@
-// tcgen05 / TMEM / TMA GEMM for sm_100a -- see gemm_sm100.cuh for the contract.
+// Device side of the tcgen05 / TMEM / TMA GEMM (sm_100a).  See gemm_sm100.cuh for the contract.
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx)
+//   warp 1      : MMA issuer     (one thread: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16, fp32 accum in TMEM)
+//   warp 2      : TMEM allocator
+//   warps 4..11 : epilogue       (tcgen05.ld 32x32b -> bias / GELU / arg-max in registers -> per-warp swizzled
+//                                 shared-memory transpose -> fully coalesced 128-byte global rows)
+// Persistent CTAs (1 per SM) walk the tile list; two TMEM accumulator stages overlap epilogue(i) with mainloop(i+1).
+#pragma once
 #include "gemm_sm100.cuh"
 #include <cuda.h>
-#include <mutex>
-#include <vector>
-#include <algorithm>
 
 namespace ec {
 
-// ============================================================================================
-// PTX wrappers (sm_100a)
-// ============================================================================================
 namespace ptx {
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -34,9 +36,6 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, int c0, int c1, uint32_t bar) {
   asm volatile(
@@ -89,6 +88,15 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 }  // namespace ptx
 
 // ============================================================================================
@@ -100,6 +108,7 @@ constexpr int kUmmaK = 16;
 constexpr int kEpiWarps = 8;        // two warps per TMEM lane quadrant (column halves)
 constexpr int kFirstEpiWarp = 4;
 constexpr int kThreads = (kFirstEpiWarp + kEpiWarps) * 32;   // 384
+constexpr int kEpiStageBytes = 32 * 32 * 4;                  // one 32x32 fp32 chunk per epilogue warp
 constexpr long long kWatchdogCycles = 4000000000LL;          // ~2 s at 2 GHz
 
 template <int BN> struct TileCfg {
@@ -109,7 +118,8 @@ template <int BN> struct TileCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;                   // two accumulator stages
   static constexpr int kBarBytes = 1024;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024 /*align slack*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + kBarBytes + 1024 /*align*/;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 
 __device__ int g_gemm_watchdog = 0;
@@ -163,13 +173,14 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     EpiParams p, int K, int tiles_m, int tiles_n) {
   using Cfg = TileCfg<BN>;
-  if (p.skip_flag != nullptr && *p.skip_flag != 0) return;
+  pdl_launch_dependents();
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a0 = smem_base;
   const uint32_t smem_b0 = smem_base + Cfg::kStages * Cfg::kABytes;
-  const uint32_t bar0 = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t smem_epi = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t bar0 = smem_epi + kEpiWarps * kEpiStageBytes;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * Cfg::kStages + s); };
@@ -183,6 +194,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + kBK - 1) / kBK;
 
+  // ---- prologue (overlaps the previous kernel's tail under programmatic dependent launch)
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_w);
@@ -207,7 +219,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 0) {
+  pdl_wait();     // from here on we touch memory written by the previous kernel
+  const bool skip = (p.skip_flag != nullptr && *p.skip_flag != 0);
+
+  if (skip) {
+    // fall through to the teardown
+  } else if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
@@ -257,6 +274,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int half = e >> 2;                  // column half of the tile
     constexpr int kColsPerWarp = BN / 2;
     constexpr int kChunks = kColsPerWarp / 32;
+    const uint32_t stg = smem_epi + (uint32_t)e * kEpiStageBytes;
     int acc = 0; uint32_t acc_phase = 0;
     int cur_len = 0;
     if (EPI == EPI_ARGMAX) cur_len = (p.cur_len != nullptr) ? *p.cur_len : (1 << 30);
@@ -264,8 +282,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
       if (!bounded_wait(tfull_bar(acc), acc_phase, 4)) break;
       ptx::tc_fence_after();
-      const int grow = m_blk * kBM + quad * 32 + lane;
-      const bool row_ok = grow < p.M;
+      const int row0 = m_blk * kBM + quad * 32;       // first global row of this warp's 32-row slab
       float best_v = -INFINITY; int best_i = 0;
 #pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
@@ -287,41 +304,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           }
         }
-        if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
-          if (EPI == EPI_BF16_GELU) {
+        if (EPI == EPI_BF16_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          }
-          if (row_ok) {
-            bf16* orow = reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo + gcol0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (gcol0 + j < p.N) {
-                uint4 q;
-                q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(orow + j) = q;
-              }
-            }
-          }
-        } else if (EPI == EPI_F32 || EPI == EPI_F32_RESID) {
-          if (row_ok) {
-            float* orow = reinterpret_cast<float*>(p.out) + (size_t)grow * p.ldo + gcol0;
-            const float* rrow = (EPI == EPI_F32_RESID) ? p.residual + (size_t)grow * p.ldr + gcol0 : nullptr;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (gcol0 + j < p.N) {
-                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                if (EPI == EPI_F32_RESID) {
-                  const float4 rr = *reinterpret_cast<const float4*>(rrow + j);
-                  o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-                }
-                *reinterpret_cast<float4*>(orow + j) = o;
-              }
-            }
-          }
-        } else {  // EPI_ARGMAX
-          if (row_ok) {
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (EPI == EPI_ARGMAX) {
+          if (row0 + lane < p.M) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int col = gcol0 + j;
@@ -332,20 +320,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (x > best_v) { best_v = x; best_i = col; }
               }
             }
-            if (p.logits != nullptr) {
-              float* lrow = p.logits + (p.cur_len != nullptr ? (size_t)(cur_len - 1) * p.logits_step_stride : 0) +
-                            (size_t)grow * p.ld_logits + gcol0;
+          }
+          if (p.logits == nullptr) continue;  // warp-uniform: nothing to store
+        }
+        // ---- transpose through shared memory: lane = row  ->  8 lanes x 16 B = one 128-byte row segment
+        //      (16-byte unit u of row r lives at unit u ^ (r & 7): conflict-free in both directions)
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (gcol0 + j < p.N)
-                  *reinterpret_cast<float4*>(lrow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int g = 0; g < 8; ++g)
+          ptx::st_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)((g ^ (lane & 7)) * 16), v[4 * g], v[4 * g + 1],
+                            v[4 * g + 2], v[4 * g + 3]);
+        __syncwarp();
+        const int cc = lane & 7;
+        const int gcol = gcol0 + cc * 4;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + (lane >> 3);
+          const int grow = row0 + rr;
+          float4 o = ptx::ld_shared_v4(stg + (uint32_t)rr * 128u + (uint32_t)((cc ^ (rr & 7)) * 16));
+          if (grow < p.M && gcol < p.N) {
+            if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
+              uint2 q;
+              q.x = pack_bf16x2(o.x, o.y);
+              q.y = pack_bf16x2(o.z, o.w);
+              *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo + gcol) = q;
+            } else if (EPI == EPI_F32 || EPI == EPI_F32_RESID) {
+              if (EPI == EPI_F32_RESID) {
+                const float4 rsd = *reinterpret_cast<const float4*>(p.residual + (size_t)grow * p.ldr + gcol);
+                o.x += rsd.x; o.y += rsd.y; o.z += rsd.z; o.w += rsd.w;
               }
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)grow * p.ldo + gcol) = o;
+            } else {  // EPI_ARGMAX with logits requested
+              float* lbase = p.logits + (p.cur_len != nullptr ? (size_t)(cur_len - 1) * p.logits_step_stride : 0);
+              *reinterpret_cast<float4*>(lbase + (size_t)grow * p.ld_logits + gcol) = o;
             }
           }
         }
+        __syncwarp();                           // staging buffer is reused by the next chunk
       }
-      if (EPI == EPI_ARGMAX && row_ok) {
-        const size_t slot = (size_t)grow * p.n_parts + (size_t)(n_blk * 2 + half);
+      if (EPI == EPI_ARGMAX && row0 + lane < p.M) {
+        const size_t slot = (size_t)(row0 + lane) * p.n_parts + (size_t)(n_blk * 2 + half);
         p.part_val[slot] = best_v;
         p.part_idx[slot] = best_i;
       }
@@ -363,215 +376,6 @@ done:
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
-}
-
-// ============================================================================================
-// Host side: tensor maps + launch
-// ============================================================================================
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
-    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<PFN_encodeTiled>(p);
-  });
-  return fn;
-}
-
-// 2-D bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle
-static int make_tmap(CUtensorMap* out, const bf16* base, int rows, int cols, int ld, int box_rows) {
-  PFN_encodeTiled fn = get_encode_fn();
-  EC_REQUIRE(fn != nullptr, EC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  EC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0, EC_ERR_INVALID, "GEMM operand not 16-byte aligned");
-  EC_REQUIRE(ld % 8 == 0, EC_ERR_INVALID, "GEMM operand row stride %d not a multiple of 8 elements", ld);
-  // descriptors are pure functions of (base, shape, stride, box): memoise them, encoding costs microseconds
-  struct Key { const void* p; int r, c, l, b; };
-  struct Entry { Key k; CUtensorMap m; };
-  static std::mutex mu;
-  static std::vector<Entry> cache[256];
-  const size_t hsh = ((reinterpret_cast<uintptr_t>(base) >> 8) ^ (size_t)rows * 131u ^ (size_t)box_rows) & 255u;
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    for (const Entry& e : cache[hsh])
-      if (e.k.p == base && e.k.r == rows && e.k.c == cols && e.k.l == ld && e.k.b == box_rows) {
-        *out = e.m;
-        return EC_OK;
-      }
-  }
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(bf16)};
-  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  EC_REQUIRE(r == CUDA_SUCCESS, EC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    if (cache[hsh].size() < 64) cache[hsh].push_back(Entry{Key{base, rows, cols, ld, box_rows}, *out});
-  }
-  return EC_OK;
-}
-
-int gemm_argmax_parts(int N) { return ceil_div(N, 256) * 2; }
-
-template <int BN, int EPI>
-static int launch_tile(const GemmArgs& a, cudaStream_t stream) {
-  using Cfg = TileCfg<BN>;
-  CUtensorMap ta, tw;
-  EC_TRY(make_tmap(&ta, a.A, a.M, a.K, a.lda, kBM));
-  EC_TRY(make_tmap(&tw, a.W, a.N, a.K, a.ldw, BN));
-  EpiParams p;
-  p.M = a.M; p.N = a.N; p.bias = a.bias; p.residual = a.residual; p.ldr = a.ldr; p.out = a.out; p.ldo = a.ldo;
-  p.logits = a.logits; p.ld_logits = a.ld_logits; p.logits_step_stride = a.logits_step_stride; p.part_val = a.part_val; p.part_idx = a.part_idx;
-  p.n_parts = a.n_parts; p.eos_col = a.eos_col; p.cur_len = a.cur_len; p.min_len = a.min_len;
-  p.skip_flag = a.skip_flag;
-  const int tiles_m = ceil_div(a.M, kBM), tiles_n = ceil_div(a.N, BN);
-  const int grid = std::min(tiles_m * tiles_n, num_sms());
-  static bool attr_set = false;   // per template instantiation
-  if (!attr_set) {
-    EC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::kSmemBytes));
-    attr_set = true;
-  }
-  gemm_tcgen05_kernel<BN, EPI><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tw, p, a.K, tiles_m, tiles_n);
-  EC_POST_LAUNCH();
-  return EC_OK;
-}
-
-template <int EPI>
-static int launch_epi(const GemmArgs& a, cudaStream_t stream) {
-  if constexpr (EPI == EPI_ARGMAX) {
-    return launch_tile<256, EPI>(a, stream);
-  } else {
-  const int sms = num_sms();
-  const int tm = ceil_div(a.M, kBM);
-  if (tm * ceil_div(a.N, 256) >= sms) return launch_tile<256, EPI>(a, stream);
-  if (tm * ceil_div(a.N, 128) >= sms / 2 || a.N >= 1024) return launch_tile<128, EPI>(a, stream);
-  return launch_tile<64, EPI>(a, stream);
-  }
-}
-
-// ---- optional per-launch timing (CUDA events on the launching stream) for the roofline line of bench.py
-struct ProfSlot { cudaEvent_t beg, end; double flops; };
-static bool g_prof_on = false;
-static std::vector<ProfSlot> g_prof_slots;
-static size_t g_prof_used = 0;
-
-void gemm_profile_enable(bool on) { g_prof_on = on; g_prof_used = 0; }
-
-int gemm_profile_read(double* ms, double* flops, long long* launches) {
-  double tms = 0.0, tf = 0.0;
-  for (size_t i = 0; i < g_prof_used; ++i) {
-    EC_CHECK_CUDA(cudaEventSynchronize(g_prof_slots[i].end));
-    float t = 0.f;
-    EC_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof_slots[i].beg, g_prof_slots[i].end));
-    tms += t;
-    tf += g_prof_slots[i].flops;
-  }
-  if (ms) *ms = tms;
-  if (flops) *flops = tf;
-  if (launches) *launches = (long long)g_prof_used;
-  g_prof_used = 0;
-  return EC_OK;
-}
-
-static int gemm_dispatch(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream);
-
-int gemm_bf16(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream) {
-  if (!g_prof_on) return gemm_dispatch(a, epi, stream);
-  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
-    return gemm_dispatch(a, epi, stream);
-  if (g_prof_used == g_prof_slots.size()) {
-    ProfSlot s{};
-    EC_CHECK_CUDA(cudaEventCreate(&s.beg));
-    EC_CHECK_CUDA(cudaEventCreate(&s.end));
-    g_prof_slots.push_back(s);
-  }
-  ProfSlot& s = g_prof_slots[g_prof_used];
-  EC_CHECK_CUDA(cudaEventRecord(s.beg, stream));
-  const int rc = gemm_dispatch(a, epi, stream);
-  EC_CHECK_CUDA(cudaEventRecord(s.end, stream));
-  if (rc == EC_OK) { s.flops = 2.0 * a.M * (double)a.N * a.K; ++g_prof_used; }
-  return rc;
-}
-
-static int gemm_dispatch(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream) {
-  EC_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, EC_ERR_INVALID, "GEMM with empty dimension M=%d N=%d K=%d", a.M, a.N, a.K);
-  // K may be ragged (TMA zero-fills the box beyond K); only row strides need 16-byte alignment
-  EC_REQUIRE(a.N % 8 == 0, EC_ERR_UNSUPPORTED, "GEMM needs N to be a multiple of 8 (N=%d)", a.N);
-  EC_REQUIRE(a.lda >= a.K && a.ldw >= a.K, EC_ERR_INVALID, "GEMM row strides shorter than K");
-  EC_REQUIRE(a.A && a.W, EC_ERR_INVALID, "GEMM null operand");
-  if (epi != EPI_ARGMAX) {
-    EC_REQUIRE(a.out != nullptr && a.ldo % 8 == 0, EC_ERR_INVALID, "GEMM output null or ldo %% 8 != 0");
-    EC_REQUIRE((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0, EC_ERR_INVALID, "GEMM output not 16-byte aligned");
-  } else {
-    EC_REQUIRE(a.part_val && a.part_idx && a.n_parts == gemm_argmax_parts(a.N), EC_ERR_INVALID,
-               "arg-max GEMM needs part buffers with n_parts=%d", gemm_argmax_parts(a.N));
-    EC_REQUIRE(a.logits == nullptr || a.ld_logits % 4 == 0, EC_ERR_INVALID, "logits row stride must be a multiple of 4");
-  }
-  if (epi == EPI_F32_RESID)
-    EC_REQUIRE(a.residual != nullptr && a.ldr % 4 == 0, EC_ERR_INVALID, "residual epilogue needs a residual pointer");
-  if (a.bias) EC_REQUIRE((reinterpret_cast<uintptr_t>(a.bias) & 15u) == 0, EC_ERR_INVALID, "bias not 16-byte aligned");
-  switch (epi) {
-    case EPI_BF16: return launch_epi<EPI_BF16>(a, stream);
-    case EPI_BF16_GELU: return launch_epi<EPI_BF16_GELU>(a, stream);
-    case EPI_F32: return launch_epi<EPI_F32>(a, stream);
-    case EPI_F32_RESID: return launch_epi<EPI_F32_RESID>(a, stream);
-    case EPI_ARGMAX: return launch_epi<EPI_ARGMAX>(a, stream);
-  }
-  set_error("unknown GEMM epilogue %d", (int)epi);
-  return EC_ERR_INVALID;
-}
-
-int gemm_check_watchdog(cudaStream_t stream) {
-  EC_CHECK_CUDA(cudaStreamSynchronize(stream));
-  int v = 0;
-  EC_CHECK_CUDA(cudaMemcpyFromSymbol(&v, g_gemm_watchdog, sizeof(int)));
-  if (v != 0) {
-    int zero = 0;
-    cudaMemcpyToSymbol(g_gemm_watchdog, &zero, sizeof(int));
-    set_error("tcgen05 GEMM pipeline wait timed out (role code %d)", v);
-    return EC_ERR_TIMEOUT;
-  }
-  return EC_OK;
-}
-
-// ============================================================================================
-// SIMT cross-check kernel (tests only)
-// ============================================================================================
-__global__ void gemm_simt_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W, int ldw, int M, int N,
-                                 int K, EpiParams p, int epi) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  const int row = blockIdx.y;
-  if (col >= N || row >= M) return;
-  float acc = 0.f;
-  for (int k = 0; k < K; ++k) acc += __bfloat162float(A[(size_t)row * lda + k]) * __bfloat162float(W[(size_t)col * ldw + k]);
-  if (p.bias) acc += p.bias[col];
-  if (epi == EPI_BF16) reinterpret_cast<bf16*>(p.out)[(size_t)row * p.ldo + col] = __float2bfloat16_rn(acc);
-  else if (epi == EPI_BF16_GELU) reinterpret_cast<bf16*>(p.out)[(size_t)row * p.ldo + col] = __float2bfloat16_rn(gelu_erf(acc));
-  else if (epi == EPI_F32) reinterpret_cast<float*>(p.out)[(size_t)row * p.ldo + col] = acc;
-  else if (epi == EPI_F32_RESID)
-    reinterpret_cast<float*>(p.out)[(size_t)row * p.ldo + col] = acc + p.residual[(size_t)row * p.ldr + col];
-  else if (p.logits) p.logits[(size_t)row * p.ld_logits + col] = acc;
-}
-
-int gemm_reference_simt(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream) {
-  EpiParams p;
-  p.M = a.M; p.N = a.N; p.bias = a.bias; p.residual = a.residual; p.ldr = a.ldr; p.out = a.out; p.ldo = a.ldo;
-  p.logits = a.logits; p.ld_logits = a.ld_logits; p.logits_step_stride = a.logits_step_stride; p.part_val = a.part_val; p.part_idx = a.part_idx;
-  p.n_parts = a.n_parts; p.eos_col = a.eos_col; p.cur_len = a.cur_len; p.min_len = a.min_len; p.skip_flag = nullptr;
-  dim3 grid(ceil_div(a.N, 128), a.M);
-  gemm_simt_kernel<<<grid, 128, 0, stream>>>(a.A, a.lda, a.W, a.ldw, a.M, a.N, a.K, p, (int)epi);
-  EC_POST_LAUNCH();
-  return EC_OK;
 }
 
 }  // namespace ec

@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, void* __restrict__ y,
                                                         long long ldy, int rows, int width,
                                                         const int* __restrict__ skip_flag) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (skip_flag != nullptr && *skip_flag != 0) return;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -82,11 +84,13 @@ int layernorm(const float* x, long long ldx, const float* gamma, const float* be
   if (rows <= 0) return EC_OK;
   const int wpb = 8;
   const int grid = ceil_div(rows, wpb);
+  note_launches(1);
   if (y_is_bf16)
-    layernorm_kernel<true><<<grid, wpb * 32, 0, stream>>>(x, ldx, gamma, beta, y, ldy, rows, width, skip_flag);
+    EC_CHECK_CUDA(launch_kernel(layernorm_kernel<true>, dim3(grid), dim3(wpb * 32), 0, stream, x, ldx, gamma, beta, y, ldy,
+                                rows, width, skip_flag));
   else
-    layernorm_kernel<false><<<grid, wpb * 32, 0, stream>>>(x, ldx, gamma, beta, y, ldy, rows, width, skip_flag);
-  EC_POST_LAUNCH();
+    EC_CHECK_CUDA(launch_kernel(layernorm_kernel<false>, dim3(grid), dim3(wpb * 32), 0, stream, x, ldx, gamma, beta, y,
+                                ldy, rows, width, skip_flag));
   return EC_OK;
 }
 
