@@ -288,6 +288,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int c = 0; c < kChunks; ++c) {
         const int col_in_tile = half * kColsPerWarp + c * 32;
         const int gcol0 = n_blk * BN + col_in_tile;
+        const int cc = lane & 7;
+        const int gcol = gcol0 + cc * 4;
+        // The residual may alias the output (in-place residual stream).  Issue all eight residual loads of this
+        // chunk up front (before the TMEM load and the transpose) so their HBM latency is hidden and the
+        // possible aliasing cannot serialise load -> store -> load.
+        float4 rsd[8];
+        if (EPI == EPI_F32_RESID) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int grow = row0 + it * 4 + (lane >> 3);
+            rsd[it] = (grow < p.M && gcol < p.N)
+                          ? *reinterpret_cast<const float4*>(p.residual + (size_t)grow * p.ldr + gcol)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col_in_tile), r);
         ptx::tmem_ld_wait();
@@ -330,8 +345,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           ptx::st_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)((g ^ (lane & 7)) * 16), v[4 * g], v[4 * g + 1],
                             v[4 * g + 2], v[4 * g + 3]);
         __syncwarp();
-        const int cc = lane & 7;
-        const int gcol = gcol0 + cc * 4;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int rr = it * 4 + (lane >> 3);
@@ -345,8 +358,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo + gcol) = q;
             } else if (EPI == EPI_F32 || EPI == EPI_F32_RESID) {
               if (EPI == EPI_F32_RESID) {
-                const float4 rsd = *reinterpret_cast<const float4*>(p.residual + (size_t)grow * p.ldr + gcol);
-                o.x += rsd.x; o.y += rsd.y; o.z += rsd.z; o.w += rsd.w;
+                o.x += rsd[it].x; o.y += rsd[it].y; o.z += rsd[it].z; o.w += rsd[it].w;
               }
               *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)grow * p.ldo + gcol) = o;
             } else {  // EPI_ARGMAX with logits requested

@@ -34,7 +34,9 @@ def main():
                                    torch.arange(args.batch, dtype=torch.int32, device=dev), None)
     lat, embs = eng.model._encode_image_dev(x)
     torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.profiler.start()
+    ev0.record()
     if args.stage in ("all",):
         eng.caption_crops(crops, keys, args.seq_len)
     elif args.stage == "encode":
@@ -42,9 +44,11 @@ def main():
     elif args.stage == "decode":
         eng.model.generate(None, image_embs=embs, generation_type="top_k", seq_len=args.seq_len,
                            fixed_output_length=True, return_logits=False)
+    ev1.record()
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
-    print("profiled stage", args.stage, "batch", args.batch)
+    print("profiled stage", args.stage, "batch", args.batch, "graph", args.graph, "PDL", os.environ.get("EC_PDL", "1"),
+          "ms", round(ev0.elapsed_time(ev1), 3))
 
 
 if __name__ == "__main__":
