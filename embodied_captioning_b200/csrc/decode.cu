@@ -46,56 +46,52 @@ int decode_embed(const int* tokens, int ld_tokens, const float* tok_emb, const f
 constexpr int kMaxKeys = 260;   // >= n_queries-1 and >= context_length+1
 
 __device__ __forceinline__ void warp_attend(const float (&qf)[8], const bf16* kbase, const bf16* vbase, size_t rstride,
-                                            int n, float* s_p, int lane, float (&acc)[8], float& inv) {
+                                            int n, int lane, float (&acc)[8], float& inv) {
+  // single pass, online softmax: K and V rows of a 16-key batch are requested together (one HBM round trip per
+  // batch instead of two dependent passes); all 32 lanes agree on the running max
   const int grp = lane >> 3;
-  float mx = -INFINITY;
+  float m = -INFINITY, l = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   for (int j0 = 0; j0 < n; j0 += 16) {
-    uint4 u[4];
+    uint4 ku[4], vu[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int j = j0 + i * 4 + grp;
-      u[i] = (j < n) ? *reinterpret_cast<const uint4*>(kbase + (size_t)j * rstride) : make_uint4(0, 0, 0, 0);
+      if (j < n) {
+        ku[i] = *reinterpret_cast<const uint4*>(kbase + (size_t)j * rstride);
+        vu[i] = *reinterpret_cast<const uint4*>(vbase + (size_t)j * rstride);
+      } else {
+        ku[i] = make_uint4(0, 0, 0, 0);
+        vu[i] = make_uint4(0, 0, 0, 0);
+      }
     }
+    float sc[4];
+    float bm = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 a0 = unpack_bf16x2(u[i].x), a1 = unpack_bf16x2(u[i].y), a2 = unpack_bf16x2(u[i].z), a3 = unpack_bf16x2(u[i].w);
+      const float2 a0 = unpack_bf16x2(ku[i].x), a1 = unpack_bf16x2(ku[i].y), a2 = unpack_bf16x2(ku[i].z), a3 = unpack_bf16x2(ku[i].w);
       float d = a0.x * qf[0] + a0.y * qf[1] + a1.x * qf[2] + a1.y * qf[3] + a2.x * qf[4] + a2.y * qf[5] +
                 a3.x * qf[6] + a3.y * qf[7];
       d += __shfl_xor_sync(0xffffffffu, d, 1);
       d += __shfl_xor_sync(0xffffffffu, d, 2);
       d += __shfl_xor_sync(0xffffffffu, d, 4);
-      const int j = j0 + i * 4 + grp;
-      if (j < n) {
-        if ((lane & 7) == 0) s_p[j] = d;
-        mx = fmaxf(mx, d);
-      }
+      sc[i] = (j0 + i * 4 + grp < n) ? d : -INFINITY;
+      bm = fmaxf(bm, sc[i]);
     }
-  }
-  mx = warp_max(mx);
-  __syncwarp();
-  float sum = 0.f;
-  for (int j = lane; j < n; j += 32) {
-    const float e = __expf(s_p[j] - mx);
-    s_p[j] = e;
-    sum += e;
-  }
-  sum = warp_sum(sum);
-  __syncwarp();
-  inv = 1.0f / sum;
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 8));
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));
+    const float mn = fmaxf(m, bm);                 // finite: every batch holds at least one valid key
+    const float corr = __expf(m - mn);             // exp(-inf) = 0 on the first batch
+    m = mn;
+    l *= corr;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int j0 = 0; j0 < n; j0 += 16) {
-    uint4 u[4];
+    for (int i = 0; i < 8; ++i) acc[i] *= corr;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int j = j0 + i * 4 + grp;
-      u[i] = (j < n) ? *reinterpret_cast<const uint4*>(vbase + (size_t)j * rstride) : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int j = j0 + i * 4 + grp;
-      const float p = (j < n) ? s_p[j] : 0.f;
-      const float2 a0 = unpack_bf16x2(u[i].x), a1 = unpack_bf16x2(u[i].y), a2 = unpack_bf16x2(u[i].z), a3 = unpack_bf16x2(u[i].w);
+      const float p = __expf(sc[i] - mn);          // 0 for masked rows
+      l += p;
+      const float2 a0 = unpack_bf16x2(vu[i].x), a1 = unpack_bf16x2(vu[i].y), a2 = unpack_bf16x2(vu[i].z), a3 = unpack_bf16x2(vu[i].w);
       acc[0] += p * a0.x; acc[1] += p * a0.y; acc[2] += p * a1.x; acc[3] += p * a1.y;
       acc[4] += p * a2.x; acc[5] += p * a2.y; acc[6] += p * a3.x; acc[7] += p * a3.y;
     }
@@ -105,6 +101,9 @@ __device__ __forceinline__ void warp_attend(const float (&qf)[8], const bf16* kb
     acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
     acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
   }
+  l += __shfl_xor_sync(0xffffffffu, l, 8);
+  l += __shfl_xor_sync(0xffffffffu, l, 16);
+  inv = 1.0f / l;
 }
 
 __device__ __forceinline__ void load_q_slice(const bf16* q, float (&qf)[8]) {
@@ -131,7 +130,6 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __res
   pdl_launch_dependents();
   pdl_wait();
   if (st->done) return;
-  __shared__ float s_p[4][kMaxKeys];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x * 4 + w;
   if (pair >= batch * heads) return;
@@ -149,7 +147,7 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __res
   load_q_slice(row, qf);
   __syncwarp();     // the appended row is read back by other lanes of this warp below
   float acc[8], inv;
-  warp_attend(qf, kc, vc, (size_t)C, pos + 1, s_p[w], lane, acc, inv);
+  warp_attend(qf, kc, vc, (size_t)C, pos + 1, lane, acc, inv);
   if (grp == 0) store_out_slice(out + (size_t)b * C + h * D + sub * 8, acc, inv);
 }
 
@@ -173,7 +171,6 @@ __global__ void __launch_bounds__(128) decode_cross_attn_kernel(const bf16* __re
   pdl_launch_dependents();
   pdl_wait();
   if (st->done) return;
-  __shared__ float s_p[4][kMaxKeys];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x * 4 + w;
   if (pair >= batch * heads) return;
@@ -185,7 +182,7 @@ __global__ void __launch_bounds__(128) decode_cross_attn_kernel(const bf16* __re
   load_q_slice(q + (size_t)b * C + h * D + sub * 8, qf);
   const bf16* kbase = kv + (size_t)b * n_kv * 2 * C + h * D + sub * 8;
   float acc[8], inv;
-  warp_attend(qf, kbase, kbase + C, (size_t)2 * C, n_kv, s_p[w], lane, acc, inv);
+  warp_attend(qf, kbase, kbase + C, (size_t)2 * C, n_kv, lane, acc, inv);
   if ((lane >> 3) == 0) store_out_slice(out + (size_t)b * C + h * D + sub * 8, acc, inv);
 }
 
