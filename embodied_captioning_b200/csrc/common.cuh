@@ -96,18 +96,24 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
 }
 
 __device__ __forceinline__ float gelu_erf(float x) {
-  // nn.GELU() exact form (coca_model.py:65): 0.5 x (1 + erf(x / sqrt(2))).  erf by Abramowitz-Stegun 7.1.26
-  // (|abs err| < 1.5e-7, far below the bf16 rounding of the stored result) -- a third of erff()'s instructions,
-  // which matters because the fc1 epilogue evaluates it 128 x 256 times per tile next to the MMA main loop.
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
+  // nn.GELU() exact (erf) form (coca_model.py:65): 0.5 x (1 + erf(x / sqrt(2))).
+  //
+  // Evaluated as x * Phi(x) with Phi(-|x|) = 0.5 erfc(|x|/sqrt 2) = 2^Q(z): Q is a degree-7 minimax fit of
+  // log2(erfc(z)) - 1 on z in [0, 4.2] (scripts of the fit: DESIGN.md section 3; max |gelu error| 5.6e-7, max
+  // relative error 3.3e-6 -- three orders below the bf16 rounding of the stored result).  One MUFU (ex2) and
+  // ten FMA-pipe instructions per element: the fc1 epilogue evaluates this 128 x 256 times per tile next to
+  // an 8192-cycle MMA main loop, so the instruction count is what bounds that GEMM.
+  const float z = fminf(fabsf(x) * 0.70710678118654752440f, 4.2f);
+  float q = fmaf(-2.074870827e-05f, z, 4.926680704e-04f);
+  q = fmaf(q, z, -5.263294093e-03f);
+  q = fmaf(q, z, 3.403032571e-02f);
+  q = fmaf(q, z, -1.526207328e-01f);
+  q = fmaf(q, z, -9.169294834e-01f);
+  q = fmaf(q, z, -1.628114700e+00f);
+  q = fmaf(q, z, -9.999952912e-01f);
+  float w;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(q));
+  return (x >= 0.f) ? fmaf(-x, w, x) : x * w;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -45,27 +45,34 @@ int decode_embed(const int* tokens, int ld_tokens, const float* tok_emb, const f
 // row (16 B each), 4 rows per warp instruction, 4 independent instructions (16 rows) in flight per lane.
 constexpr int kMaxKeys = 260;   // >= n_queries-1 and >= context_length+1
 
+__device__ __forceinline__ void attend_load(const bf16* kbase, const bf16* vbase, size_t rstride, int n, int j0, int grp,
+                                            uint4 (&ku)[4], uint4 (&vu)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = j0 + i * 4 + grp;
+    if (j < n) {
+      ku[i] = *reinterpret_cast<const uint4*>(kbase + (size_t)j * rstride);
+      vu[i] = *reinterpret_cast<const uint4*>(vbase + (size_t)j * rstride);
+    } else {
+      ku[i] = make_uint4(0, 0, 0, 0);
+      vu[i] = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
 __device__ __forceinline__ void warp_attend(const float (&qf)[8], const bf16* kbase, const bf16* vbase, size_t rstride,
                                             int n, int lane, float (&acc)[8], float& inv) {
-  // single pass, online softmax: K and V rows of a 16-key batch are requested together (one HBM round trip per
-  // batch instead of two dependent passes); all 32 lanes agree on the running max
+  // Single pass with an online softmax.  K and V rows of a 16-key batch are requested together and the next
+  // batch is prefetched into registers before the current one is reduced (software pipelining), so one HBM
+  // round trip is exposed per kernel instead of one per batch.  All 32 lanes agree on the running max.
   const int grp = lane >> 3;
   float m = -INFINITY, l = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  uint4 ku[4], vu[4], kn[4], vn[4];
+  attend_load(kbase, vbase, rstride, n, 0, grp, ku, vu);
   for (int j0 = 0; j0 < n; j0 += 16) {
-    uint4 ku[4], vu[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int j = j0 + i * 4 + grp;
-      if (j < n) {
-        ku[i] = *reinterpret_cast<const uint4*>(kbase + (size_t)j * rstride);
-        vu[i] = *reinterpret_cast<const uint4*>(vbase + (size_t)j * rstride);
-      } else {
-        ku[i] = make_uint4(0, 0, 0, 0);
-        vu[i] = make_uint4(0, 0, 0, 0);
-      }
-    }
+    attend_load(kbase, vbase, rstride, n, j0 + 16, grp, kn, vn);     // prefetch (all-masked past the end)
     float sc[4];
     float bm = -INFINITY;
 #pragma unroll
@@ -95,6 +102,8 @@ __device__ __forceinline__ void warp_attend(const float (&qf)[8], const bf16* kb
       acc[0] += p * a0.x; acc[1] += p * a0.y; acc[2] += p * a1.x; acc[3] += p * a1.y;
       acc[4] += p * a2.x; acc[5] += p * a2.y; acc[6] += p * a3.x; acc[7] += p * a3.y;
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ku[i] = kn[i]; vu[i] = vn[i]; }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
