@@ -27,6 +27,13 @@ BATCH = int(os.environ.get("EC_BENCH_BATCH", "1024"))
 SEQ_LEN = 30
 VIEWS = 8                        # views per object instance in the synthetic batch
 ENC_GFLOP = {"coca_ViT-L-14": 163.64, "coca_ViT-B-32": 9.19}     # SURVEY.md section 8(a) A3, per crop
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def load_peaks():
@@ -127,7 +134,7 @@ def run_reference(args, rank, world):
     dt = time.time() - t0
     v = per_step * args.steps / dt
     sample = f"{per_step} of {BATCH} crops per step, batch-1 re-forward generate (no KV cache), fp32"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -135,7 +142,7 @@ def run_reference(args, rank, world):
                                f"(CPU reference path, bounded sample)", "sample_crops_per_step": per_step},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def main():
@@ -147,6 +154,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner there) are sent to
+    # stderr for the whole run and the line is written to the saved descriptor at the end
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -231,8 +244,17 @@ def main():
     def step_host():
         if world == 1:
             return eng.caption_crops_host(crops_host, keys_host, SEQ_LEN)
-        r = eng.caption_crops_host(crops_host, keys_host, SEQ_LEN)       # local shard; exchange below
-        return r
+        # N > 1: H2D of the local shard, local captioning, NCCL exchange + reduction, D2H of tokens and scores
+        c = crops_host.to(dev, non_blocking=True)
+        k = keys_host.to(dev, non_blocking=True)
+        x, _, _ = ops.preprocess_crops(c, eng_rects, eng_fi, None, size=cfg.image_size)
+        o = eng.caption_preprocessed(x, None, SEQ_LEN)
+        ik, isc, _ = D.allgather_disagreement(o["latent"], k, BATCH * world, 0)
+        tok = o["tokens"].cpu()
+        sc = isc.cpu()
+        ikc = ik.cpu()
+        return {"h2d_bytes": crops_host.numel() + keys_host.numel() * 8,
+                "d2h_bytes": tok.numel() * 8 + sc.numel() * 4 + ikc.numel() * 8}
     step_host()
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -293,7 +315,7 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, sd)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

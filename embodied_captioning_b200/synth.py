@@ -185,3 +185,40 @@ def make_frames_and_boxes(n_frames: int, boxes_per_frame: int, height: int = 480
     frame_idx = np.repeat(np.arange(n_frames, dtype=np.int32), boxes_per_frame)
     keys = np.tile(np.arange(boxes_per_frame, dtype=np.int64), n_frames)
     return frames, boxes, frame_idx, keys
+
+
+def make_instance_crops(n_instances: int, views: int, size: int = 224, seed: int = 5678, view_noise: float = 6.0):
+    """Multi-view shaped input: `views` noisy, slightly shifted views of each of `n_instances` base crops.
+    Returns (uint8 [n_instances*views, size, size, 3], instance ids int64 [n_instances*views])."""
+    base = make_crops(n_instances, size=size + 16, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    out = np.empty((n_instances * views, size, size, 3), dtype=np.uint8)
+    ids = np.repeat(np.arange(n_instances, dtype=np.int64), views)
+    for i in range(n_instances):
+        for v in range(views):
+            dx, dy = rng.integers(0, 17, size=2)
+            img = base[i, dy:dy + size, dx:dx + size].astype(np.float32)
+            img += rng.normal(0, view_noise, size=img.shape)
+            out[i * views + v] = np.clip(img, 0, 255).astype(np.uint8)
+    return out, ids
+
+
+def fit_confident_head(hidden: torch.Tensor, targets: torch.Tensor, vocab_size: int, margin: float = 12.0,
+                       ridge: float = 1e-3) -> torch.Tensor:
+    """Closed-form "training" of the vocabulary head on given decoder states.
+
+    Random-init weights give almost flat 49k-way logits, so greedy arg-max is decided by numerical noise.  A
+    trained captioner is confident; this emulates that cheaply: given final-LayerNorm states `hidden` [S, T]
+    (one per (crop, position)) and the token each state should emit, `targets` [S], it solves the ridge
+    regression  P = argmin |hidden P - margin * onehot(targets)|^2 + ridge |P|^2  and returns P [T, vocab]
+    (a drop-in `text_decoder.text_projection`), rounded to bf16-representable values.
+    """
+    H = hidden.to(torch.float64)
+    S, T = H.shape
+    A = H.t() @ H
+    A += ridge * float(A.diagonal().mean()) * torch.eye(T, dtype=torch.float64)
+    # H^T Y with Y = margin * onehot: column v collects the states whose target is v
+    HtY = torch.zeros((T, vocab_size), dtype=torch.float64)
+    HtY.index_add_(1, targets.to(torch.long), (H * margin).t().contiguous())
+    P = torch.linalg.solve(A, HtY)
+    return _bf16_round(P.to(torch.float32))

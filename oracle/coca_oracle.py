@@ -181,6 +181,17 @@ class OracleCoCa:
         x = self._ln(x, "text_decoder.ln_final")
         return self._lin(x, sd["text_decoder.text_projection"].t())
 
+    def decoder_hidden(self, image_embs: torch.Tensor, text: torch.Tensor) -> torch.Tensor:
+        """ln_final output of the multimodal decoder for every position of `text` ([B,t,T]); the vocabulary
+        projection of these states is `forward_logits`.  Used to fit the trained-like head of the parity tests."""
+        cfg = self.cfg
+        x = self.text_tokens(text)
+        mask = self._causal(x.shape[1])
+        for i in range(cfg.mm_layers):
+            x = self._block(x, f"text_decoder.resblocks.{i}", cfg.mm_heads, mask)
+            x = self._cross_block(x, image_embs, f"text_decoder.cross_attn.{i}", cfg.mm_heads)
+        return self._ln(x, "text_decoder.ln_final")
+
     def forward_logits(self, image_embs, text):
         """coca_model.py:170-203 with output_labels=False -> logits [B,t,V]."""
         return self.decoder_logits(image_embs, self.text_tokens(text))
