@@ -23,7 +23,7 @@ EXPORTS = [
     "ec_encode_image", "ec_decode_workspace_bytes", "ec_decode_greedy", "ec_forward_logits",
     "ec_disagreement_workspace_bytes", "ec_instance_disagreement", "ec_instance_disagreement_peers",
     "ec_gemm_bf16", "ec_gemm_argmax", "ec_layernorm", "ec_attention", "ec_check_watchdog",
-    "ec_launch_count", "ec_profile_gemm", "ec_profile_gemm_read",
+    "ec_launch_count", "ec_profile_gemm", "ec_profile_gemm_read", "ec_attention_fused_qkv",
 ]
 
 
@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
     L.ec_layernorm.argtypes = [vp, i64, vp, vp, vp, i64, i32, i32, i32, vp]
     L.ec_attention.argtypes = [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64, i32, i32, i32, i32, i32, vp]
     L.ec_check_watchdog.argtypes = [vp]
+    L.ec_attention_fused_qkv.argtypes = [vp, i64, i32, i32, i32, vp, i64, i64, i32, i32, i32, i32, i32, vp]
     L.ec_launch_count.argtypes = []
     L.ec_launch_count.restype = C.c_int64
     L.ec_profile_gemm.argtypes = [i32]

@@ -52,6 +52,7 @@ class CoCa(nn.Module):
         self._ws: Dict[str, torch.Tensor] = {}
         self._state_dict_ref: Optional[Dict[str, torch.Tensor]] = None
         self._graph = False
+        self._tc_attention = True
         self._dummy = nn.Parameter(torch.zeros(1), requires_grad=False)   # lets `.parameters()` work
 
     # ------------------------------------------------------------------ nn.Module protocol
@@ -111,11 +112,18 @@ class CoCa(nn.Module):
         nat.check(nat.lib().ec_model_create(C.byref(ec), self._device.index or 0, C.byref(self._handle)),
                   "ec_model_create")
         nat.check(nat.lib().ec_model_set_option(self._handle, b"decode_graph", int(self._graph)), "ec_model_set_option")
+        nat.check(nat.lib().ec_model_set_option(self._handle, b"tc_attention", int(self._tc_attention)))
 
     def set_decode_graph(self, enabled: bool):
         self._graph = bool(enabled)
         if self._handle:
             nat.check(nat.lib().ec_model_set_option(self._handle, b"decode_graph", int(self._graph)))
+
+    def set_tc_attention(self, enabled: bool):
+        """ViT-block attention on tcgen05/TMEM (default) or on the mma.sync flash kernel."""
+        self._tc_attention = bool(enabled)
+        if self._handle:
+            nat.check(nat.lib().ec_model_set_option(self._handle, b"tc_attention", int(self._tc_attention)))
 
     def load_state_dict(self, state_dict, strict: bool = True):
         """open_clip-layout tensors (names/shapes: SURVEY.md Appendix A); `module.` prefixes are stripped like

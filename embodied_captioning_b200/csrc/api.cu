@@ -65,6 +65,7 @@ int ec_model_finalize(ec_model* m, void* stream) {
 int ec_model_set_option(ec_model* m, const char* key, int value) {
   EC_REQUIRE(m && key, EC_ERR_INVALID, "null argument");
   if (!strcmp(key, "decode_graph")) { m->impl.use_graph = value != 0; return EC_OK; }
+  if (!strcmp(key, "tc_attention")) { m->impl.use_tc_attention = value != 0; return EC_OK; }
   set_error("unknown option %s", key);
   return EC_ERR_INVALID;
 }
@@ -188,7 +189,30 @@ int ec_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64
   return attention_full(a, as_stream(stream));
 }
 
-int ec_check_watchdog(void* stream) { return gemm_check_watchdog(as_stream(stream)); }
+int ec_check_watchdog(void* stream) {
+  EC_TRY(gemm_check_watchdog(as_stream(stream)));
+  return attention_sm100_check_watchdog(as_stream(stream));
+}
+
+int ec_attention_fused_qkv(const void* qkv, int64_t ld, int32_t q_col0, int32_t k_col0, int32_t v_col0, void* out,
+                           int64_t o_bs, int64_t o_rs, int32_t batch, int32_t heads, int32_t seq, int32_t head_dim,
+                           int32_t impl, void* stream) {
+  EC_REQUIRE(qkv && out, EC_ERR_INVALID, "ec_attention_fused_qkv: null argument");
+  const bf16* base = reinterpret_cast<const bf16*>(qkv);
+  if (impl == 1) {
+    EC_REQUIRE(attention_sm100_supported(seq, head_dim), EC_ERR_UNSUPPORTED,
+               "tcgen05 attention supports head_dim 64 and seq <= 258 (got %d, %d)", head_dim, seq);
+    return attention_sm100_fused_qkv(base, ld, q_col0, k_col0, v_col0, reinterpret_cast<bf16*>(out), o_bs, o_rs, batch,
+                                     heads, seq, as_stream(stream));
+  }
+  AttnArgs a{};
+  a.q = base + q_col0; a.k = base + k_col0; a.v = base + v_col0;
+  a.q_bs = a.k_bs = a.v_bs = (long long)seq * ld; a.q_rs = a.k_rs = a.v_rs = ld;
+  a.o = reinterpret_cast<bf16*>(out); a.o_bs = o_bs; a.o_rs = o_rs;
+  a.batch = batch; a.heads = heads; a.sq = seq; a.skv = seq; a.head_dim = head_dim;
+  a.scale = 1.0f / sqrtf((float)head_dim);
+  return attention_full(a, as_stream(stream));
+}
 
 int64_t ec_launch_count(void) { return (int64_t)launch_count(); }
 

@@ -1,0 +1,475 @@
+// ViT self-attention on the 5th-gen tensor cores (sm_100a): S = Q K^T and O = P V as tcgen05.mma with the
+// accumulators, the probabilities and the output all living in TMEM.
+//
+// One persistent CTA per SM walks (crop, head) pairs.  Per pair: K and V of the head (<= 272 keys x 64) are staged
+// once by TMA (128B swizzle); every 128-query tile then runs
+//     QK^T  : tcgen05.mma  M=128, N=n_mma (<=256), K=64   A = Q tile (smem, K-major), B = K (smem, K-major) -> S (TMEM fp32)
+//     softmax: one thread per query row (tcgen05.ld 32x32b: no shuffles), exp2 with the scale folded in,
+//              P written back IN PLACE over S as packed bf16 (tcgen05.st), the row sum kept in registers
+//     PV    : tcgen05.mma  M=128, N=64, K=n_mma         A = P (TMEM), B = V (smem, MN-major)            -> O (TMEM fp32,
+//              columns [128,192) of the same buffer, free once the softmax has consumed S)
+//     epilogue: O / rowsum -> bf16 -> global (row of 128 B per thread)
+// Two S/P/O buffers (2 x 256 TMEM columns) and two softmax warpgroups ping-pong so the tensor core computes
+// QK^T of tile i+1 while the CUDA cores run the softmax of tile i.  ViT-L/14 has 257 tokens: keys 0..255 go
+// through the tensor core, the 257th key (and up to 15 more) is folded in by the row's own thread in fp32.
+//
+//   warp 0: TMA producer | warp 1: MMA issuer | warp 2: TMEM allocator | warps 4-7: softmax/epilogue group 0
+//   | warps 8-11: group 1
+#include "kernels.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace ec {
+
+namespace aptx {
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+}  // namespace aptx
+
+constexpr int kAD = 64;                  // head dim
+constexpr int kATile = 128;              // query rows per tile (UMMA M)
+constexpr int kAKeysMma = 256;           // keys handled by the tensor core (UMMA N limit)
+constexpr int kAKeysTail = 16;           // rows of the TMA box that carries the keys beyond 256
+constexpr int kATailMax = 2;             // extra keys (beyond 256) folded in by the row's own thread in fp32
+constexpr int kAThreads = 12 * 32;
+constexpr int kAKBytes = (kAKeysMma + kAKeysTail) * kAD * 2;     // 34816: K (or V) of one head, 272 rows x 128 B
+constexpr int kAQBytes = kATile * kAD * 2;                        // 16384
+constexpr int kASmemBytes = 2 * 2 * kAKBytes + 2 * kAQBytes + 1024 + 1024;
+constexpr int kATmemCols = 512;          // two S/P/O buffers of 256 columns
+constexpr long long kAWatchdog = 4000000000LL;
+
+__device__ int g_attn_watchdog = 0;
+
+__device__ __forceinline__ bool await(uint32_t bar, uint32_t parity, int code) {
+  if (aptx::mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!aptx::mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kAWatchdog) { atomicExch(&g_attn_watchdog, code); return false; }
+  }
+  return true;
+}
+
+// K-major SW128 operand (rows of 128 B, 8-row atoms 1024 B apart)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// MN-major SW128 operand: 64 contiguous N elements (128 B) per K row, 8 K rows per 1024-B atom (SBO), one N chunk
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint32_t idesc_qk(int n) {       // bf16 x bf16 -> f32, M=128, N=n, both K-major
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kATile >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t idesc_pv() {            // M=128, N=64, A K-major (TMEM), B MN-major
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(kAD >> 3) << 17) | ((uint32_t)(kATile >> 4) << 24);
+}
+
+struct AttnSm100Args {
+  bf16* out; long long o_bs, o_rs;      // out[b*o_bs + s*o_rs + h*64 + d]
+  int batch, heads, seq;                // seq = queries = keys (<= 272)
+  int q_col0, k_col0, v_col0;           // first column of q / k / v inside the fused row
+  float scale_log2;                     // (1/sqrt(64)) * log2(e)
+};
+
+__global__ void __launch_bounds__(kAThreads, 1)
+attention_sm100_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16,
+                       AttnSm100Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto k_smem = [&](int buf) { return base + (uint32_t)buf * 2u * kAKBytes; };
+  auto v_smem = [&](int buf) { return base + (uint32_t)buf * 2u * kAKBytes + kAKBytes; };
+  auto q_smem = [&](int buf) { return base + 4u * kAKBytes + (uint32_t)buf * kAQBytes; };
+  const uint32_t bar0 = base + 4u * kAKBytes + 2u * kAQBytes;
+  // barriers (8 B each): kv_full[2] kv_empty[2] q_full[2] q_empty[2] s_full[2] p_ready[2] o_full[2] s_empty[2]
+  auto BAR = [&](int which, int i) { return bar0 + 8u * (uint32_t)(which * 2 + i); };
+  enum { KV_FULL = 0, KV_EMPTY, Q_FULL, Q_EMPTY, S_FULL, P_READY, O_FULL, S_EMPTY };
+  const uint32_t tmem_slot = bar0 + 8u * 16u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_pairs = a.batch * a.heads;
+  const int n_qtiles = (a.seq + kATile - 1) / kATile;
+  const int n_mma = min((a.seq + 15) & ~15, kAKeysMma);          // keys through the tensor core (multiple of 16)
+  const int n_valid_mma = min(a.seq, kAKeysMma);
+  const int n_tail = a.seq - n_valid_mma;                         // 0..16 keys handled in fp32 by the row threads
+  const bool tail_box = a.seq > kAKeysMma;
+
+  if (warp == 0 && lane == 0) { aptx::prefetch_tmap(&tm128); aptx::prefetch_tmap(&tm16); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      aptx::mbar_init(BAR(KV_FULL, i), 1);
+      aptx::mbar_init(BAR(KV_EMPTY, i), 1);           // commit after the last PV of the pair
+      aptx::mbar_init(BAR(Q_FULL, i), 1);
+      aptx::mbar_init(BAR(Q_EMPTY, i), n_tail > 0 ? 1 + 128 : 1);   // QK^T commit (+ the row threads' tail-key dots)
+      aptx::mbar_init(BAR(S_FULL, i), 1);
+      aptx::mbar_init(BAR(P_READY, i), 128);
+      aptx::mbar_init(BAR(O_FULL, i), 1);
+      aptx::mbar_init(BAR(S_EMPTY, i), 128);
+    }
+    aptx::fence_barrier_init();
+  }
+  if (warp == 2) { aptx::tmem_alloc(tmem_slot, kATmemCols); aptx::tmem_relinquish(); }
+  aptx::tc_fence_before();
+  __syncthreads();
+  aptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      uint32_t kv_it = 0, q_it = 0;
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        const int b = pair / a.heads, h = pair % a.heads;
+        const int row0 = b * a.seq;
+        const int kvb = kv_it & 1;
+        if (!await(BAR(KV_EMPTY, kvb), ((kv_it >> 1) & 1) ^ 1u, 1)) goto done;
+        const int kv_boxes = (n_mma + kATile - 1) / kATile;
+        aptx::mbar_expect_tx(BAR(KV_FULL, kvb), (uint32_t)(2 * (kv_boxes * kAQBytes + (tail_box ? kAKeysTail * 128 : 0))));
+        for (int i = 0; i < kv_boxes; ++i) {
+          aptx::tma_load_2d(k_smem(kvb) + i * kAQBytes, &tm128, a.k_col0 + h * kAD, row0 + i * kATile, BAR(KV_FULL, kvb));
+          aptx::tma_load_2d(v_smem(kvb) + i * kAQBytes, &tm128, a.v_col0 + h * kAD, row0 + i * kATile, BAR(KV_FULL, kvb));
+        }
+        if (tail_box) {
+          aptx::tma_load_2d(k_smem(kvb) + 2 * kAQBytes, &tm16, a.k_col0 + h * kAD, row0 + kAKeysMma, BAR(KV_FULL, kvb));
+          aptx::tma_load_2d(v_smem(kvb) + 2 * kAQBytes, &tm16, a.v_col0 + h * kAD, row0 + kAKeysMma, BAR(KV_FULL, kvb));
+        }
+        ++kv_it;
+        for (int t = 0; t < n_qtiles; ++t, ++q_it) {
+          const int qb = q_it & 1;
+          if (!await(BAR(Q_EMPTY, qb), ((q_it >> 1) & 1) ^ 1u, 2)) goto done;
+          aptx::mbar_expect_tx(BAR(Q_FULL, qb), kAQBytes);
+          aptx::tma_load_2d(q_smem(qb), &tm128, a.q_col0 + h * kAD, row0 + t * kATile, BAR(Q_FULL, qb));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t id_qk = idesc_qk(n_mma), id_pv = idesc_pv();
+      uint32_t kv_it = 0, it = 0;            // `it` counts q tiles globally: buffers alternate with it & 1
+      int prev_valid = 0; uint32_t prev_it = 0; int prev_kvb = 0; bool prev_last = false;
+      auto issue_pv = [&](uint32_t pit, int pkvb, bool last_of_pair) -> bool {
+        const int sb = pit & 1;
+        if (!await(BAR(P_READY, sb), (pit >> 1) & 1, 5)) return false;
+        aptx::tc_fence_after();
+        const uint32_t t_p = tmem_base + (uint32_t)(sb * 256);
+        const uint32_t t_o = t_p + 128;
+        for (int k = 0; k < n_mma / 16; ++k)
+          aptx::umma_ts(t_o, t_p + (uint32_t)(k * 8), desc_mnmajor(v_smem(pkvb) + (uint32_t)k * 2048u), id_pv, k > 0 ? 1u : 0u);
+        aptx::umma_commit(BAR(O_FULL, sb));
+        if (last_of_pair) aptx::umma_commit(BAR(KV_EMPTY, pkvb));
+        return true;
+      };
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        const int kvb = kv_it & 1;
+        if (!await(BAR(KV_FULL, kvb), (kv_it >> 1) & 1, 3)) goto done;
+        for (int t = 0; t < n_qtiles; ++t, ++it) {
+          const int sb = it & 1;
+          if (!await(BAR(S_EMPTY, sb), ((it >> 1) & 1) ^ 1u, 4)) goto done;
+          if (!await(BAR(Q_FULL, sb), (it >> 1) & 1, 6)) goto done;
+          aptx::tc_fence_after();
+          const uint32_t t_s = tmem_base + (uint32_t)(sb * 256);
+#pragma unroll
+          for (int k = 0; k < kAD / 16; ++k)
+            aptx::umma_ss(t_s, desc_kmajor(q_smem(sb)) + (uint64_t)(k * 2), desc_kmajor(k_smem(kvb)) + (uint64_t)(k * 2),
+                          id_qk, k > 0 ? 1u : 0u);
+          aptx::umma_commit(BAR(S_FULL, sb));
+          aptx::umma_commit(BAR(Q_EMPTY, sb));
+          if (prev_valid) { if (!issue_pv(prev_it, prev_kvb, prev_last)) goto done; }
+          prev_valid = 1; prev_it = it; prev_kvb = kvb; prev_last = (t == n_qtiles - 1);
+        }
+        ++kv_it;
+      }
+      if (prev_valid) issue_pv(prev_it, prev_kvb, prev_last);
+    }
+  } else if (warp >= 4) {
+    // ============================================================ softmax + epilogue (one thread per query row)
+    const int grp = (warp - 4) >> 2;          // buffer / tile parity this warpgroup serves
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;           // row inside the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    uint32_t kv_it = 0, it = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++kv_it) {
+      const int b = pair / a.heads, h = pair % a.heads;
+      const int kvb = kv_it & 1;
+      bool kv_waited = false;
+      for (int t = 0; t < n_qtiles; ++t, ++it) {
+        if ((int)(it & 1) != grp) continue;
+        const int sb = grp;
+        const uint32_t par = (it >> 1) & 1;
+        const int qrow = t * kATile + r;
+        const bool row_ok = qrow < a.seq;
+        // ---- tail keys (beyond the 256 the tensor core handles): fp32 dot products by the row's own thread
+        float s_tail[kATailMax] = {0.f, 0.f};
+        if (n_tail > 0) {
+          if (!kv_waited) { if (!await(BAR(KV_FULL, kvb), (kv_it >> 1) & 1, 7)) goto done; kv_waited = true; }
+          if (!await(BAR(Q_FULL, sb), par, 8)) goto done;
+          float q[kAD];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 u = aptx::ld_shared_u4(q_smem(sb) + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) * 16));
+            const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+            q[c * 8 + 0] = f0.x; q[c * 8 + 1] = f0.y; q[c * 8 + 2] = f1.x; q[c * 8 + 3] = f1.y;
+            q[c * 8 + 4] = f2.x; q[c * 8 + 5] = f2.y; q[c * 8 + 6] = f3.x; q[c * 8 + 7] = f3.y;
+          }
+#pragma unroll
+          for (int j = 0; j < kATailMax; ++j) {
+            if (j >= n_tail) break;
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint4 u = aptx::ld_shared_u4(k_smem(kvb) + 2u * kAQBytes + (uint32_t)j * 128u + (uint32_t)((c ^ (j & 7)) * 16));
+              const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+              acc += q[c * 8 + 0] * f0.x + q[c * 8 + 1] * f0.y + q[c * 8 + 2] * f1.x + q[c * 8 + 3] * f1.y +
+                     q[c * 8 + 4] * f2.x + q[c * 8 + 5] * f2.y + q[c * 8 + 6] * f3.x + q[c * 8 + 7] * f3.y;
+            }
+            s_tail[j] = acc;
+          }
+        }
+        if (n_tail > 0) aptx::mbar_arrive(BAR(Q_EMPTY, sb));   // this thread no longer needs the Q tile
+        // ---- S ready
+        if (!await(BAR(S_FULL, sb), par, 9)) goto done;
+        aptx::tc_fence_after();
+        const uint32_t t_s = tmem_base + lane_addr + (uint32_t)(sb * 256);
+        float mx = -INFINITY;
+        for (int c0 = 0; c0 < n_mma; c0 += 32) {
+          uint32_t v[32];
+          aptx::tmem_ld32(t_s + (uint32_t)c0, v);
+          aptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < n_valid_mma) mx = fmaxf(mx, __uint_as_float(v[j]));
+        }
+#pragma unroll
+        for (int j = 0; j < kATailMax; ++j)
+          if (j < n_tail) mx = fmaxf(mx, s_tail[j]);
+        const float ms = mx * a.scale_log2;
+        float sum = 0.f;
+        for (int c0 = 0; c0 < n_mma; c0 += 32) {
+          uint32_t v[32];
+          aptx::tmem_ld32(t_s + (uint32_t)c0, v);
+          aptx::tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = (c0 + j < n_valid_mma) ? aptx::ex2(fmaf(__uint_as_float(v[j]), a.scale_log2, -ms)) : 0.f;
+            const float p1 = (c0 + j + 1 < n_valid_mma) ? aptx::ex2(fmaf(__uint_as_float(v[j + 1]), a.scale_log2, -ms)) : 0.f;
+            sum += p0 + p1;
+            pk[j >> 1] = pack_bf16x2(p0, p1);
+          }
+          aptx::tmem_st16(t_s + (uint32_t)(c0 >> 1), pk);   // P overwrites the S columns already consumed
+        }
+        // tail keys: their P.V contribution is formed now, so every direct read of the pair's K/V tiles by this
+        // thread happens before its P_READY arrive (the last PV commit of the pair then safely frees the tiles)
+        float o[kAD];
+#pragma unroll
+        for (int j = 0; j < kAD; ++j) o[j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < kATailMax; ++j) {
+          if (j >= n_tail) break;
+          const float p = aptx::ex2(fmaf(s_tail[j], a.scale_log2, -ms));
+          sum += p;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 u = aptx::ld_shared_u4(v_smem(kvb) + 2u * kAQBytes + (uint32_t)j * 128u + (uint32_t)((c ^ (j & 7)) * 16));
+            const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+            o[c * 8 + 0] += p * f0.x; o[c * 8 + 1] += p * f0.y; o[c * 8 + 2] += p * f1.x; o[c * 8 + 3] += p * f1.y;
+            o[c * 8 + 4] += p * f2.x; o[c * 8 + 5] += p * f2.y; o[c * 8 + 6] += p * f3.x; o[c * 8 + 7] += p * f3.y;
+          }
+        }
+        aptx::tmem_st_wait();
+        aptx::tc_fence_before();
+        aptx::mbar_arrive(BAR(P_READY, sb));
+        // ---- O ready
+        if (!await(BAR(O_FULL, sb), par, 10)) goto done;
+        aptx::tc_fence_after();
+        {
+          uint32_t v[32];
+          aptx::tmem_ld32(t_s + 128u, v);
+          aptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] += __uint_as_float(v[j]);
+          aptx::tmem_ld32(t_s + 160u, v);
+          aptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[32 + j] += __uint_as_float(v[j]);
+        }
+        aptx::tc_fence_before();
+        aptx::mbar_arrive(BAR(S_EMPTY, sb));             // buffer free for the QK^T of tile it+2
+        if (row_ok) {
+          const float inv = 1.0f / sum;
+          bf16* orow = a.out + (size_t)b * a.o_bs + (size_t)qrow * a.o_rs + (size_t)h * kAD;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4 u;
+            u.x = pack_bf16x2(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv); u.y = pack_bf16x2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
+            u.z = pack_bf16x2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv); u.w = pack_bf16x2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
+            *reinterpret_cast<uint4*>(orow + c * 8) = u;
+          }
+        }
+      }
+    }
+  }
+done:
+  aptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { aptx::tc_fence_after(); aptx::tmem_dealloc(tmem_base, kATmemCols); }
+}
+
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiledA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_map(CUtensorMap* out, const bf16* base, long long rows, int cols, long long ld, int box_rows) {
+  static PFN_encodeTiledA fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiledA>(p);
+  });
+  EC_REQUIRE(fn != nullptr, EC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(bf16)};
+  cuuint32_t box[2] = {(cuuint32_t)kAD, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EC_REQUIRE(r == CUDA_SUCCESS, EC_ERR_CUDA, "cuTensorMapEncodeTiled (attention) failed with CUresult %d", (int)r);
+  return EC_OK;
+}
+
+bool attention_sm100_supported(int seq, int head_dim) {
+  return head_dim == kAD && seq >= 1 && seq <= kAKeysMma + kATailMax;
+}
+
+int attention_sm100_fused_qkv(const bf16* qkv, long long ld, int q_col0, int k_col0, int v_col0, bf16* out,
+                              long long o_bs, long long o_rs, int batch, int heads, int seq, cudaStream_t stream) {
+  EC_REQUIRE(attention_sm100_supported(seq, kAD), EC_ERR_UNSUPPORTED, "tcgen05 attention: seq %d unsupported", seq);
+  EC_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15u) == 0, EC_ERR_INVALID, "tcgen05 attention: alignment");
+  EC_REQUIRE(o_rs % 8 == 0 && o_bs % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0, EC_ERR_INVALID,
+             "tcgen05 attention: output alignment");
+  const long long rows = (long long)batch * seq;
+  const int cols = std::max(std::max(q_col0, k_col0), v_col0) + heads * kAD;
+  EC_REQUIRE(cols <= ld, EC_ERR_INVALID, "tcgen05 attention: column slices exceed the row stride");
+  CUtensorMap tm128, tm16;
+  EC_TRY(encode_map(&tm128, qkv, rows, cols, ld, kATile));
+  EC_TRY(encode_map(&tm16, qkv, rows, cols, ld, kAKeysTail));
+  static bool attr = false;
+  if (!attr) {
+    EC_CHECK_CUDA(cudaFuncSetAttribute(attention_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kASmemBytes));
+    attr = true;
+  }
+  AttnSm100Args a;
+  a.out = out; a.o_bs = o_bs; a.o_rs = o_rs; a.batch = batch; a.heads = heads; a.seq = seq;
+  a.q_col0 = q_col0; a.k_col0 = k_col0; a.v_col0 = v_col0;
+  a.scale_log2 = 0.125f * 1.4426950408889634f;
+  const int grid = std::min(batch * heads, num_sms());
+  attention_sm100_kernel<<<grid, kAThreads, kASmemBytes, stream>>>(tm128, tm16, a);
+  EC_POST_LAUNCH();
+  return EC_OK;
+}
+
+int attention_sm100_check_watchdog(cudaStream_t stream) {
+  EC_CHECK_CUDA(cudaStreamSynchronize(stream));
+  int v = 0;
+  EC_CHECK_CUDA(cudaMemcpyFromSymbol(&v, g_attn_watchdog, sizeof(int)));
+  if (v != 0) {
+    int zero = 0;
+    cudaMemcpyToSymbol(g_attn_watchdog, &zero, sizeof(int));
+    set_error("tcgen05 attention pipeline wait timed out (role code %d)", v);
+    return EC_ERR_TIMEOUT;
+  }
+  return EC_OK;
+}
+
+}  // namespace ec

@@ -313,7 +313,10 @@ int Model::encode_image(const bf16* x, int n, float* latent, float* embs, void* 
     a.o = w.att; a.o_bs = (long long)TV * W; a.o_rs = W;
     a.batch = n; a.heads = heads; a.sq = TV; a.skv = TV; a.head_dim = cfg.vision_head_dim;
     a.scale = 1.0f / sqrtf((float)cfg.vision_head_dim);
-    EC_TRY(attention_full(a, s));
+    if (use_tc_attention && attention_sm100_supported(TV, cfg.vision_head_dim))
+      EC_TRY(attention_sm100_fused_qkv(w.qkv, 3 * W, 0, W, 2 * W, w.att, (long long)TV * W, W, n, heads, TV, s));
+    else
+      EC_TRY(attention_full(a, s));
     EC_TRY(linear(w.att, W, b.w_out, W, b.b_out, Mv, W, W, w.resid, W, EPI_F32_RESID, w.resid, W, nullptr, s));
     EC_TRY(layernorm(w.resid, W, b.ln2_g, b.ln2_b, w.ln, W, true, Mv, W, nullptr, s));
     EC_TRY(linear(w.ln, W, b.w_fc1, W, b.b_fc1, Mv, 4 * W, W, w.fc1, 4 * W, EPI_BF16_GELU, nullptr, 0, nullptr, s));

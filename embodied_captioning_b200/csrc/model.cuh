@@ -23,6 +23,7 @@ struct Model {
   int device;
   bool finalized = false;
   bool use_graph = false;
+  bool use_tc_attention = false;   // tcgen05/TMEM attention for the ViT blocks (option "tc_attention")
   int patch_k = 0, patch_ld = 0;
 
   // vision tower

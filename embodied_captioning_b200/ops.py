@@ -87,6 +87,19 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> 
     return out
 
 
+def attention_fused_qkv(qkv: torch.Tensor, heads: int, impl: int = 1) -> torch.Tensor:
+    """qkv bf16 [B, S, 3*H*D] (q | k | v column blocks) -> [B, S, H*D]; impl 1 = tcgen05/TMEM kernel, 0 = mma.sync."""
+    _check_dev(qkv)
+    assert qkv.dtype == torch.bfloat16 and qkv.dim() == 3 and qkv.is_contiguous()
+    B, S, C3 = qkv.shape
+    C = C3 // 3
+    out = torch.empty((B, S, C), device=qkv.device, dtype=torch.bfloat16)
+    with torch.cuda.device(qkv.device):
+        nat.check(nat.lib().ec_attention_fused_qkv(qkv.data_ptr(), C3, 0, C, 2 * C, out.data_ptr(), S * C, C, B, heads, S,
+                                                   C // heads, impl, _stream(qkv)), "ec_attention_fused_qkv")
+    return out
+
+
 def preprocess_crops(frames: torch.Tensor, rects: torch.Tensor, frame_idx: torch.Tensor,
                      flags: Optional[torch.Tensor] = None, size: int = 224, want_f32: bool = False,
                      want_bf16: bool = True):

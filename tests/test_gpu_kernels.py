@@ -124,3 +124,26 @@ def test_attention_strided_fused_qkv_and_shared_queries(device):
     out2 = ops.attention(q, qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H)
     ref2 = ops.attention(q.unsqueeze(0).expand(B, -1, -1).contiguous(), qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H)
     assert torch.equal(out2, ref2)
+
+
+@pytest.mark.parametrize("B,H,S", [(3, 16, 257), (2, 12, 50), (2, 4, 256), (2, 4, 258), (5, 3, 130), (1, 1, 17),
+                                   (1, 2, 1), (300, 2, 257)])
+def test_attention_tcgen05_fused_qkv(device, B, H, S):
+    """ViT-block attention on tcgen05/TMEM (S = QK^T, P and O in tensor memory) vs an fp32 reference and vs the
+    mma.sync kernel, on the fused [B, S, 3*H*64] layout of the image tower."""
+    D = 64
+    C = H * D
+    qkv = _rand_bf16((B, S, 3 * C), device, seed=31)
+    out = ops.attention_fused_qkv(qkv, H, impl=1)
+    ops.check_watchdog(device)
+    legacy = ops.attention_fused_qkv(qkv, H, impl=0)
+    qf = qkv[:, :, :C].float().view(B, S, H, D).transpose(1, 2)
+    kf = qkv[:, :, C:2 * C].float().view(B, S, H, D).transpose(1, 2)
+    vf = qkv[:, :, 2 * C:].float().view(B, S, H, D).transpose(1, 2)
+    p = torch.softmax(qf @ kf.transpose(-1, -2) / D ** 0.5, dim=-1)
+    ref = (p @ vf).transpose(1, 2).reshape(B, S, C)
+    err = (out.float() - ref).abs().max().item()
+    rel = ((out.float() - ref).norm() / ref.norm()).item()
+    rel_legacy = ((legacy.float() - ref).norm() / ref.norm()).item()
+    print(f"tcgen05 attention B={B} H={H} S={S}: max err {err:.4f}, rel {rel:.2e} (mma.sync kernel rel {rel_legacy:.2e})")
+    assert err < 0.03 and rel < 1e-2

@@ -125,6 +125,18 @@ def test_greedy_tokens_vs_oracle(tiny, device):
         assert ((g[fin] - r[fin]).norm() / r[fin].norm()).item() < 3e-2
 
 
+def test_tcgen05_and_mma_attention_paths_agree(device):
+    """The image tower with the tcgen05/TMEM attention (default) and with the mma.sync kernel."""
+    cfg, sd, x, model = _setup("coca_ViT-B-32", 6, device)
+    lat_tc, embs_tc = model._encode_image(x.to(device))
+    model.set_tc_attention(False)
+    lat_mma, embs_mma = model._encode_image(x.to(device))
+    model.set_tc_attention(True)
+    ops.check_watchdog(device)
+    assert torch.nn.functional.cosine_similarity(lat_tc, lat_mma).min().item() > 0.9999
+    assert ((embs_tc - embs_mma).norm() / embs_mma.norm()).item() < 5e-3
+
+
 def test_cuda_graph_decode_is_identical(tiny, device):
     cfg, sd, x, model = tiny
     embs = model._encode_image(x.to(device))[1]
