@@ -65,6 +65,8 @@ def main():
     qkv = torch.randn(B, 257, 3072, device=dev).to(torch.bfloat16)
     ms = timeit(lambda: ops.attention(qkv[:, :, :1024], qkv[:, :, 1024:2048], qkv[:, :, 2048:], 16))
     out["attention"].append({"name": "vit_l14_self", "ms": ms, "tflops": 4.0 * B * 16 * 257 * 257 * 64 / ms / 1e9})
+    ms = timeit(lambda: ops.attention_fused_qkv(qkv, 16, impl=1))
+    out["attention"].append({"name": "vit_l14_self_tcgen05", "ms": ms, "tflops": 4.0 * B * 16 * 257 * 257 * 64 / ms / 1e9})
     kv = torch.randn(B, 257, 1536, device=dev).to(torch.bfloat16)
     q = torch.randn(256, 768, device=dev).to(torch.bfloat16)
     ms = timeit(lambda: ops.attention(q, kv[:, :, :768], kv[:, :, 768:], 8))
