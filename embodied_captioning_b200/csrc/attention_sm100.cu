@@ -284,31 +284,37 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
         const uint32_t par = (it >> 1) & 1;
         const int qrow = t * kATile + r;
         const bool row_ok = qrow < a.seq;
+        if (t * kATile + quad * 32 >= a.seq) {
+          // no valid query row in this warp's 32-row slab (last tile of a 257-token sequence): keep the barrier
+          // protocol in lock-step, skip all the arithmetic; the P/O rows of these lanes are never stored
+          if (n_tail > 0) {
+            if (!await(BAR(Q_FULL, sb), par, 8)) goto done;
+            aptx::mbar_arrive(BAR(Q_EMPTY, sb));
+          }
+          if (!await(BAR(S_FULL, sb), par, 9)) goto done;
+          aptx::mbar_arrive(BAR(P_READY, sb));
+          if (!await(BAR(O_FULL, sb), par, 10)) goto done;
+          aptx::mbar_arrive(BAR(S_EMPTY, sb));
+          continue;
+        }
         // ---- tail keys (beyond the 256 the tensor core handles): fp32 dot products by the row's own thread
         float s_tail[kATailMax] = {0.f, 0.f};
         if (n_tail > 0) {
           if (!kv_waited) { if (!await(BAR(KV_FULL, kvb), (kv_it >> 1) & 1, 7)) goto done; kv_waited = true; }
           if (!await(BAR(Q_FULL, sb), par, 8)) goto done;
-          float q[kAD];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const uint4 u = aptx::ld_shared_u4(q_smem(sb) + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) * 16));
-            const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-            q[c * 8 + 0] = f0.x; q[c * 8 + 1] = f0.y; q[c * 8 + 2] = f1.x; q[c * 8 + 3] = f1.y;
-            q[c * 8 + 4] = f2.x; q[c * 8 + 5] = f2.y; q[c * 8 + 6] = f3.x; q[c * 8 + 7] = f3.y;
-          }
+            const uint4 uq = aptx::ld_shared_u4(q_smem(sb) + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) * 16));
+            const float2 q0 = unpack_bf16x2(uq.x), q1 = unpack_bf16x2(uq.y), q2 = unpack_bf16x2(uq.z), q3 = unpack_bf16x2(uq.w);
 #pragma unroll
-          for (int j = 0; j < kATailMax; ++j) {
-            if (j >= n_tail) break;
-            float acc = 0.f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint4 u = aptx::ld_shared_u4(k_smem(kvb) + 2u * kAQBytes + (uint32_t)j * 128u + (uint32_t)((c ^ (j & 7)) * 16));
-              const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-              acc += q[c * 8 + 0] * f0.x + q[c * 8 + 1] * f0.y + q[c * 8 + 2] * f1.x + q[c * 8 + 3] * f1.y +
-                     q[c * 8 + 4] * f2.x + q[c * 8 + 5] * f2.y + q[c * 8 + 6] * f3.x + q[c * 8 + 7] * f3.y;
+            for (int j = 0; j < kATailMax; ++j) {
+              if (j < n_tail) {
+                const uint4 u = aptx::ld_shared_u4(k_smem(kvb) + 2u * kAQBytes + (uint32_t)j * 128u + (uint32_t)((c ^ (j & 7)) * 16));
+                const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+                s_tail[j] += q0.x * f0.x + q0.y * f0.y + q1.x * f1.x + q1.y * f1.y + q2.x * f2.x + q2.y * f2.y +
+                             q3.x * f3.x + q3.y * f3.y;
+              }
             }
-            s_tail[j] = acc;
           }
         }
         if (n_tail > 0) aptx::mbar_arrive(BAR(Q_EMPTY, sb));   // this thread no longer needs the Q tile
@@ -316,33 +322,57 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
         if (!await(BAR(S_FULL, sb), par, 9)) goto done;
         aptx::tc_fence_after();
         const uint32_t t_s = tmem_base + lane_addr + (uint32_t)(sb * 256);
+        // Both passes over the S row keep one tcgen05.ld in flight while the previous 32 columns are processed.
         float mx = -INFINITY;
-        for (int c0 = 0; c0 < n_mma; c0 += 32) {
-          uint32_t v[32];
-          aptx::tmem_ld32(t_s + (uint32_t)c0, v);
-          aptx::tmem_ld_wait();
+        {
+          uint32_t va[32], vb[32];
+          aptx::tmem_ld32(t_s, va);
+          for (int c0 = 0; c0 < n_mma; c0 += 64) {
+            aptx::tmem_ld_wait();
+            const bool has_b = c0 + 32 < n_mma;
+            if (has_b) aptx::tmem_ld32(t_s + (uint32_t)(c0 + 32), vb);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < n_valid_mma) mx = fmaxf(mx, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < n_valid_mma) mx = fmaxf(mx, __uint_as_float(va[j]));
+            if (has_b) {
+              aptx::tmem_ld_wait();
+              if (c0 + 64 < n_mma) aptx::tmem_ld32(t_s + (uint32_t)(c0 + 64), va);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c0 + 32 + j < n_valid_mma) mx = fmaxf(mx, __uint_as_float(vb[j]));
+            }
+          }
         }
 #pragma unroll
         for (int j = 0; j < kATailMax; ++j)
           if (j < n_tail) mx = fmaxf(mx, s_tail[j]);
         const float ms = mx * a.scale_log2;
         float sum = 0.f;
-        for (int c0 = 0; c0 < n_mma; c0 += 32) {
-          uint32_t v[32];
-          aptx::tmem_ld32(t_s + (uint32_t)c0, v);
-          aptx::tmem_ld_wait();
-          uint32_t pk[16];
+        {
+          uint32_t va[32], vb[32];
+          auto emit = [&](const uint32_t (&v)[32], int c0) {
+            uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float p0 = (c0 + j < n_valid_mma) ? aptx::ex2(fmaf(__uint_as_float(v[j]), a.scale_log2, -ms)) : 0.f;
-            const float p1 = (c0 + j + 1 < n_valid_mma) ? aptx::ex2(fmaf(__uint_as_float(v[j + 1]), a.scale_log2, -ms)) : 0.f;
-            sum += p0 + p1;
-            pk[j >> 1] = pack_bf16x2(p0, p1);
+            for (int j = 0; j < 32; j += 2) {
+              const float p0 = (c0 + j < n_valid_mma) ? aptx::ex2(fmaf(__uint_as_float(v[j]), a.scale_log2, -ms)) : 0.f;
+              const float p1 = (c0 + j + 1 < n_valid_mma) ? aptx::ex2(fmaf(__uint_as_float(v[j + 1]), a.scale_log2, -ms)) : 0.f;
+              sum += p0 + p1;
+              pk[j >> 1] = pack_bf16x2(p0, p1);
+            }
+            aptx::tmem_st16(t_s + (uint32_t)(c0 >> 1), pk);   // P overwrites S columns that were already consumed
+          };
+          aptx::tmem_ld32(t_s, va);
+          for (int c0 = 0; c0 < n_mma; c0 += 64) {
+            aptx::tmem_ld_wait();
+            const bool has_b = c0 + 32 < n_mma;
+            if (has_b) aptx::tmem_ld32(t_s + (uint32_t)(c0 + 32), vb);
+            emit(va, c0);
+            if (has_b) {
+              aptx::tmem_ld_wait();
+              if (c0 + 64 < n_mma) aptx::tmem_ld32(t_s + (uint32_t)(c0 + 64), va);
+              emit(vb, c0 + 32);
+            }
           }
-          aptx::tmem_st16(t_s + (uint32_t)(c0 >> 1), pk);   // P overwrites the S columns already consumed
         }
         // tail keys: their P.V contribution is formed now, so every direct read of the pair's K/V tiles by this
         // thread happens before its P_READY arrive (the last PV commit of the pair then safely frees the tiles)
