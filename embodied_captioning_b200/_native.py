@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libec_b200.so")
+LIB_PATH = os.environ.get("EC_LIB_PATH") or os.path.join(_HERE, "libec_b200.so")   # override: A/B builds only
 
 EC_OK = 0
 ERROR_NAMES = {-1: "EC_ERR_INVALID", -2: "EC_ERR_CUDA", -3: "EC_ERR_UNSUPPORTED", -4: "EC_ERR_WORKSPACE",

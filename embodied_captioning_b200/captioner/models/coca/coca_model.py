@@ -53,6 +53,7 @@ class CoCa(nn.Module):
         self._state_dict_ref: Optional[Dict[str, torch.Tensor]] = None
         self._graph = False
         self._tc_attention = True
+        self._chains = 0
         self._dummy = nn.Parameter(torch.zeros(1), requires_grad=False)   # lets `.parameters()` work
 
     # ------------------------------------------------------------------ nn.Module protocol
@@ -113,11 +114,18 @@ class CoCa(nn.Module):
                   "ec_model_create")
         nat.check(nat.lib().ec_model_set_option(self._handle, b"decode_graph", int(self._graph)), "ec_model_set_option")
         nat.check(nat.lib().ec_model_set_option(self._handle, b"tc_attention", int(self._tc_attention)))
+        nat.check(nat.lib().ec_model_set_option(self._handle, b"decode_chains", self._chains))
 
     def set_decode_graph(self, enabled: bool):
         self._graph = bool(enabled)
         if self._handle:
             nat.check(nat.lib().ec_model_set_option(self._handle, b"decode_graph", int(self._graph)))
+
+    def set_decode_chains(self, chains: int):
+        """Independent row chains of the decoder step (0 = choose from the batch size)."""
+        self._chains = int(chains)
+        if self._handle:
+            nat.check(nat.lib().ec_model_set_option(self._handle, b"decode_chains", self._chains))
 
     def set_tc_attention(self, enabled: bool):
         """ViT-block attention on tcgen05/TMEM (default) or on the mma.sync flash kernel."""

@@ -65,6 +65,11 @@ int ec_model_finalize(ec_model* m, void* stream) {
 int ec_model_set_option(ec_model* m, const char* key, int value) {
   EC_REQUIRE(m && key, EC_ERR_INVALID, "null argument");
   if (!strcmp(key, "decode_graph")) { m->impl.use_graph = value != 0; return EC_OK; }
+  if (!strcmp(key, "decode_chains")) {
+    EC_REQUIRE(value >= 0 && value <= kMaxChains, EC_ERR_INVALID, "decode_chains must be in [0, %d]", kMaxChains);
+    m->impl.decode_chains = value;
+    return EC_OK;
+  }
   if (!strcmp(key, "tc_attention")) { m->impl.use_tc_attention = value != 0; return EC_OK; }
   set_error("unknown option %s", key);
   return EC_ERR_INVALID;

@@ -17,5 +17,5 @@ done
 rc=0
 for p in "${pids[@]:-}"; do if [ -n "$p" ]; then wait "$p" || rc=1; fi; done
 [ $rc -eq 0 ] || { echo "compile failed" >&2; exit 1; }
-$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o ../libec_b200.so build/*.o -lcudart_static -ldl -lrt -lpthread
-echo "built $(realpath ../libec_b200.so)"
+$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o ${EC_LIB_OUT:-../libec_b200.so} build/*.o -lcudart_static -ldl -lrt -lpthread
+echo "built $(realpath ${EC_LIB_OUT:-../libec_b200.so})"

@@ -56,6 +56,16 @@ long long launch_count();
 // until the previous grid has completed and its writes are visible.  Without the attribute both are no-ops.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Where the trigger sits: at the top of a kernel the dependent grid is released as soon as every CTA of this grid
+// has started (its CTAs then compete for SM slots with this grid's later waves); at the bottom (default) only the
+// launch latency and the dependent's prologue overlap this grid's tail.
+#ifdef EC_PDL_EARLY
+__device__ __forceinline__ void pdl_trigger_top() { pdl_launch_dependents(); }
+__device__ __forceinline__ void pdl_trigger_bottom() {}
+#else
+__device__ __forceinline__ void pdl_trigger_top() {}
+__device__ __forceinline__ void pdl_trigger_bottom() { pdl_launch_dependents(); }
+#endif
 
 bool pdl_enabled();   // EC_PDL=1 enables (round-1 measurement: 150 ms vs 137 ms decode with it on, so default off)
 

@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(256) decode_embed_kernel(const int* __restrict
                                                            const float* __restrict__ tok_emb,
                                                            const float* __restrict__ pos_emb, float* __restrict__ x,
                                                            int batch, int width, const DecodeState* __restrict__ st) {
-  pdl_launch_dependents();
+  pdl_trigger_top();
   pdl_wait();
   if (st->done) return;
   const int pos = st->cur_len - 1;
@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(256) decode_embed_kernel(const int* __restrict
     const float4 p = __ldg(reinterpret_cast<const float4*>(pos_emb + (size_t)pos * width) + c);
     reinterpret_cast<float4*>(x + (size_t)b * width)[c] = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
   }
+  pdl_trigger_bottom();
 }
 
 int decode_embed(const int* tokens, int ld_tokens, const float* tok_emb, const float* pos_emb, float* x, int batch,
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __res
                                                                const unsigned char* __restrict__ finished,
                                                                const DecodeState* __restrict__ st) {
   constexpr int D = 64;
-  pdl_launch_dependents();
+  pdl_trigger_top();
   pdl_wait();
   if (st->done) return;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __res
   __syncwarp();     // the appended row is read back by other lanes of this warp below
   float acc[8], inv;
   warp_attend(qf, kc, vc, (size_t)C, pos + 1, lane, acc, inv);
+  pdl_trigger_bottom();
   if (grp == 0) store_out_slice(out + (size_t)b * C + h * D + sub * 8, acc, inv);
 }
 
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(128) decode_cross_attn_kernel(const bf16* __re
                                                                 const unsigned char* __restrict__ finished,
                                                                 const DecodeState* __restrict__ st) {
   constexpr int D = 64;
-  pdl_launch_dependents();
+  pdl_trigger_top();
   pdl_wait();
   if (st->done) return;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(128) decode_cross_attn_kernel(const bf16* __re
   const bf16* kbase = kv + (size_t)b * n_kv * 2 * C + h * D + sub * 8;
   float acc[8], inv;
   warp_attend(qf, kbase, kbase + C, (size_t)2 * C, n_kv, lane, acc, inv);
+  pdl_trigger_bottom();
   if ((lane >> 3) == 0) store_out_slice(out + (size_t)b * C + h * D + sub * 8, acc, inv);
 }
 
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(256) decode_select_kernel(const float* __restr
                                                             int* __restrict__ tokens, int ld_tokens,
                                                             unsigned char* __restrict__ finished, int batch,
                                                             int seq_len, int eos, int pad, DecodeState* st) {
-  pdl_launch_dependents();
+  pdl_trigger_top();
   pdl_wait();
   if (st->done) return;
   const int lane = threadIdx.x & 31;
@@ -236,6 +239,7 @@ __global__ void __launch_bounds__(256) decode_select_kernel(const float* __restr
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
   }
+  pdl_trigger_bottom();
   if (lane == 0) {
     int tok = (cur_len + 1 == seq_len) ? eos : bi;    // forced EOS at the last slot (coca_model.py:317-318)
     tokens[(size_t)b * ld_tokens + cur_len] = tok;
@@ -254,7 +258,7 @@ int decode_select(const float* part_val, const int* part_idx, int n_parts, int* 
 }
 
 __global__ void decode_advance_kernel(DecodeState* st, int teacher_forced, int batch) {
-  pdl_launch_dependents();
+  pdl_trigger_top();
   pdl_wait();
   if (st->done) return;
   st->cur_len += 1;
@@ -277,7 +281,7 @@ __global__ void __launch_bounds__(256) decode_init_kernel(int* __restrict__ toke
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / seq_len), c = (int)(i % seq_len);
-    tokens[(size_t)b * ld_tokens + c] = (c == 0) ? sot : pad;
+    if (tokens != nullptr) tokens[(size_t)b * ld_tokens + c] = (c == 0) ? sot : pad;   // null: table preset (teacher forcing)
     if (c == 0) finished[b] = 0;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {

@@ -88,8 +88,41 @@ static int launch_tile(const GemmArgs& a, cudaStream_t stream) {
   return EC_OK;
 }
 
+template <int BN, int EPI>
+static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
+  using Cfg = PairCfg<BN>;
+  CUtensorMap ta, tw;
+  EC_TRY(make_tmap(&ta, a.A, a.M, a.K, a.lda, kBM));
+  EC_TRY(make_tmap(&tw, a.W, a.N, a.K, a.ldw, BN / 2));
+  EpiParams p;
+  p.M = a.M; p.N = a.N; p.bias = a.bias; p.residual = a.residual; p.ldr = a.ldr; p.out = a.out; p.ldo = a.ldo;
+  p.logits = a.logits; p.ld_logits = a.ld_logits; p.logits_step_stride = a.logits_step_stride; p.part_val = a.part_val; p.part_idx = a.part_idx;
+  p.n_parts = a.n_parts; p.eos_col = a.eos_col; p.cur_len = a.cur_len; p.min_len = a.min_len;
+  p.skip_flag = a.skip_flag;
+  const int tiles_m = ceil_div(a.M, 2 * kBM), tiles_n = ceil_div(a.N, BN);
+  const int clusters = std::min(tiles_m * tiles_n, num_sms() / 2);
+  static bool attr_set = false;   // per template instantiation
+  if (!attr_set) {
+    EC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  note_launches(1);
+  EC_CHECK_CUDA(launch_kernel(gemm_tcgen05_pair_kernel<BN, EPI>, dim3(2 * clusters), dim3(kThreads),
+                              (size_t)Cfg::kSmemBytes, stream, ta, tw, p, a.K, tiles_m, tiles_n));
+  return EC_OK;
+}
+
+// CTA-pair (cta_group::2) kernel for GEMMs with enough 256 x 256 tiles to occupy every SM pair
+static bool use_pair_kernel(const GemmArgs& a) {
+  static const int mode = [] { const char* e = getenv("EC_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+  if (mode == 0) return false;
+  return ceil_div(a.M, 2 * kBM) * ceil_div(a.N, 256) >= num_sms() / 2;
+}
+
 template <int EPI>
 static int launch_epi(const GemmArgs& a, cudaStream_t stream) {
+  if (use_pair_kernel(a)) return launch_pair<256, EPI>(a, stream);
   if constexpr (EPI == EPI_ARGMAX) {
     return launch_tile<256, EPI>(a, stream);
   } else {

@@ -86,6 +86,57 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
+// ---- cta_group::2 (CTA-pair) forms
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// TMA load whose completion bytes are credited to an mbarrier of the pair's leader CTA (shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* tmap, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(leader_bar)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 per CTA] * B[BN rows: BN/2 per CTA]; issued by the leader CTA only
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all previously issued MMAs retired) on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask)
+               : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
@@ -168,12 +219,117 @@ struct EpiParams {
   const int* skip_flag;
 };
 
+// Epilogue of one 128 x BN accumulator tile for one epilogue warp: its 32-row TMEM lane quadrant (`quad`), the
+// column half `half`, 32 columns at a time: tcgen05.ld -> bias / GELU / arg-max in registers -> swizzled
+// shared-memory transpose -> coalesced 128-byte global row segments.  `row0` = first global row of the slab.
+// residual rows of one 32 x 32 chunk for this lane: 8 row groups x (4 columns at `gcol`)
+__device__ __forceinline__ void load_resid_chunk(const EpiParams& p, int row0, int gcol, int lane, float4 (&rsd)[8]) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int grow = row0 + it * 4 + (lane >> 3);
+    rsd[it] = (grow < p.M && gcol < p.N)
+                  ? *reinterpret_cast<const float4*>(p.residual + (size_t)grow * p.ldr + gcol)
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_acc, int row0, int n_blk, int quad,
+                                              int half, int lane, uint32_t stg, int cur_len) {
+  constexpr int kColsPerWarp = BN / 2;
+  constexpr int kChunks = kColsPerWarp / 32;
+  float best_v = -INFINITY; int best_i = 0;
+#pragma unroll 1
+  for (int c = 0; c < kChunks; ++c) {
+    const int col_in_tile = half * kColsPerWarp + c * 32;
+    const int gcol0 = n_blk * BN + col_in_tile;
+    const int cc = lane & 7;
+    const int gcol = gcol0 + cc * 4;
+    // The residual may alias the output (in-place residual stream): every element is read and written by the same
+    // thread.  All eight loads of the chunk are issued before the TMEM load and the transpose so that their latency
+    // is hidden (prefetching a whole chunk further ahead measured no better: 822 vs 842 TFLOP/s on out_proj).
+    float4 rsd[8];
+    if (EPI == EPI_F32_RESID) load_resid_chunk(p, row0, gcol, lane, rsd);
+    uint32_t r[32];
+    ptx::tmem_ld_32x32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)col_in_tile, r);
+    ptx::tmem_ld_wait();
+    if (gcol0 >= p.N) continue;           // warp-uniform
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (gcol0 + j < p.N) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol0 + j));
+          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+      }
+    }
+    if (EPI == EPI_BF16_GELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    }
+    if (EPI == EPI_ARGMAX) {
+      if (row0 + lane < p.M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = gcol0 + j;
+          if (col < p.N) {
+            float x = v[j];
+            if (col == p.eos_col && cur_len < p.min_len) x = -INFINITY;
+            v[j] = x;
+            if (x > best_v) { best_v = x; best_i = col; }
+          }
+        }
+      }
+      if (p.logits == nullptr) continue;  // warp-uniform: nothing to store
+    }
+    // ---- transpose through shared memory: lane = row  ->  8 lanes x 16 B = one 128-byte row segment
+    //      (16-byte unit u of row r lives at unit u ^ (r & 7): conflict-free in both directions)
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      ptx::st_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)((g ^ (lane & 7)) * 16), v[4 * g], v[4 * g + 1],
+                        v[4 * g + 2], v[4 * g + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3);
+      const int grow = row0 + rr;
+      float4 o = ptx::ld_shared_v4(stg + (uint32_t)rr * 128u + (uint32_t)((cc ^ (rr & 7)) * 16));
+      if (grow < p.M && gcol < p.N) {
+        if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
+          uint2 q;
+          q.x = pack_bf16x2(o.x, o.y);
+          q.y = pack_bf16x2(o.z, o.w);
+          *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo + gcol) = q;
+        } else if (EPI == EPI_F32 || EPI == EPI_F32_RESID) {
+          if (EPI == EPI_F32_RESID) {
+            o.x += rsd[it].x; o.y += rsd[it].y; o.z += rsd[it].z; o.w += rsd[it].w;
+          }
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)grow * p.ldo + gcol) = o;
+        } else {  // EPI_ARGMAX with logits requested
+          float* lbase = p.logits + (p.cur_len != nullptr ? (size_t)(cur_len - 1) * p.logits_step_stride : 0);
+          *reinterpret_cast<float4*>(lbase + (size_t)grow * p.ld_logits + gcol) = o;
+        }
+      }
+    }
+    __syncwarp();                           // staging buffer is reused by the next chunk
+
+  }
+  if (EPI == EPI_ARGMAX && row0 + lane < p.M) {
+    const size_t slot = (size_t)(row0 + lane) * p.n_parts + (size_t)(n_blk * 2 + half);
+    p.part_val[slot] = best_v;
+    p.part_idx[slot] = best_i;
+  }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     EpiParams p, int K, int tiles_m, int tiles_n) {
   using Cfg = TileCfg<BN>;
-  pdl_launch_dependents();
+  pdl_trigger_top();
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -272,8 +428,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int e = warp - kFirstEpiWarp;
     const int quad = warp & 3;                // TMEM lane quadrant this warp may access
     const int half = e >> 2;                  // column half of the tile
-    constexpr int kColsPerWarp = BN / 2;
-    constexpr int kChunks = kColsPerWarp / 32;
     const uint32_t stg = smem_epi + (uint32_t)e * kEpiStageBytes;
     int acc = 0; uint32_t acc_phase = 0;
     int cur_len = 0;
@@ -282,104 +436,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
       if (!bounded_wait(tfull_bar(acc), acc_phase, 4)) break;
       ptx::tc_fence_after();
-      const int row0 = m_blk * kBM + quad * 32;       // first global row of this warp's 32-row slab
-      float best_v = -INFINITY; int best_i = 0;
-#pragma unroll 1
-      for (int c = 0; c < kChunks; ++c) {
-        const int col_in_tile = half * kColsPerWarp + c * 32;
-        const int gcol0 = n_blk * BN + col_in_tile;
-        const int cc = lane & 7;
-        const int gcol = gcol0 + cc * 4;
-        // The residual may alias the output (in-place residual stream).  Issue all eight residual loads of this
-        // chunk up front (before the TMEM load and the transpose) so their HBM latency is hidden and the
-        // possible aliasing cannot serialise load -> store -> load.
-        float4 rsd[8];
-        if (EPI == EPI_F32_RESID) {
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int grow = row0 + it * 4 + (lane >> 3);
-            rsd[it] = (grow < p.M && gcol < p.N)
-                          ? *reinterpret_cast<const float4*>(p.residual + (size_t)grow * p.ldr + gcol)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col_in_tile), r);
-        ptx::tmem_ld_wait();
-        if (gcol0 >= p.N) continue;           // warp-uniform
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (gcol0 + j < p.N) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          }
-        }
-        if (EPI == EPI_BF16_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (EPI == EPI_ARGMAX) {
-          if (row0 + lane < p.M) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = gcol0 + j;
-              if (col < p.N) {
-                float x = v[j];
-                if (col == p.eos_col && cur_len < p.min_len) x = -INFINITY;
-                v[j] = x;
-                if (x > best_v) { best_v = x; best_i = col; }
-              }
-            }
-          }
-          if (p.logits == nullptr) continue;  // warp-uniform: nothing to store
-        }
-        // ---- transpose through shared memory: lane = row  ->  8 lanes x 16 B = one 128-byte row segment
-        //      (16-byte unit u of row r lives at unit u ^ (r & 7): conflict-free in both directions)
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          ptx::st_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)((g ^ (lane & 7)) * 16), v[4 * g], v[4 * g + 1],
-                            v[4 * g + 2], v[4 * g + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + (lane >> 3);
-          const int grow = row0 + rr;
-          float4 o = ptx::ld_shared_v4(stg + (uint32_t)rr * 128u + (uint32_t)((cc ^ (rr & 7)) * 16));
-          if (grow < p.M && gcol < p.N) {
-            if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
-              uint2 q;
-              q.x = pack_bf16x2(o.x, o.y);
-              q.y = pack_bf16x2(o.z, o.w);
-              *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo + gcol) = q;
-            } else if (EPI == EPI_F32 || EPI == EPI_F32_RESID) {
-              if (EPI == EPI_F32_RESID) {
-                o.x += rsd[it].x; o.y += rsd[it].y; o.z += rsd[it].z; o.w += rsd[it].w;
-              }
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)grow * p.ldo + gcol) = o;
-            } else {  // EPI_ARGMAX with logits requested
-              float* lbase = p.logits + (p.cur_len != nullptr ? (size_t)(cur_len - 1) * p.logits_step_stride : 0);
-              *reinterpret_cast<float4*>(lbase + (size_t)grow * p.ld_logits + gcol) = o;
-            }
-          }
-        }
-        __syncwarp();                           // staging buffer is reused by the next chunk
-      }
-      if (EPI == EPI_ARGMAX && row0 + lane < p.M) {
-        const size_t slot = (size_t)(row0 + lane) * p.n_parts + (size_t)(n_blk * 2 + half);
-        p.part_val[slot] = best_v;
-        p.part_idx[slot] = best_i;
-      }
+      epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m_blk * kBM + quad * 32, n_blk, quad, half, lane, stg,
+                             cur_len);
       // release the accumulator stage back to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    pdl_trigger_bottom();    // per-CTA trigger: the first epilogue warp that has stored its last tile
   }
 done:
   ptx::tc_fence_before();
@@ -387,6 +452,165 @@ done:
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ============================================================================================
+// CTA-pair kernel: tcgen05.mma.cta_group::2, UMMA 256 x BN x 16 over two SMs of one cluster
+// ============================================================================================
+// Each CTA of the pair stages its own 128 rows of A and HALF of the W tile (BN/2 rows) per k-block -- 32 KB instead
+// of 48 KB per 128 x 256 x 64 of math for BN = 256 -- which is what bounds the 1-CTA kernel (L2 -> SM bytes and the
+// shared-memory operand reads of the tensor pipe).  The leader CTA (cluster rank 0) issues every MMA; both CTAs' TMA
+// loads credit the leader's `full` barrier; the leader's tcgen05.commit multicasts the `empty` / `accumulator full`
+// arrivals to both CTAs; both CTAs' epilogue warps release the accumulator stage on the leader's barrier.
+template <int BN> struct PairCfg {
+  static constexpr int kABytes = kBM * kBK * 2;                // this CTA's 128 rows
+  static constexpr int kBBytes = (BN / 2) * kBK * 2;           // this CTA's half of the W tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 6 : 8;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + kBarBytes + 1024 /*align*/;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
+};
+
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t make_idesc_pair() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * kBM) >> 4) << 24);
+}
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                         EpiParams p, int K, int tiles_m, int tiles_n) {
+  using Cfg = PairCfg<BN>;
+  pdl_trigger_top();
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // identical offset in both CTAs
+  const uint32_t smem_a0 = smem_base;
+  const uint32_t smem_b0 = smem_base + Cfg::kStages * Cfg::kABytes;
+  const uint32_t smem_epi = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t bar0 = smem_epi + kEpiWarps * kEpiStageBytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * Cfg::kStages + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * Cfg::kStages + 2 + s); };
+  const uint32_t tmem_slot = bar0 + 8u * (2 * Cfg::kStages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();          // 0 = leader
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+  const int num_tiles = tiles_m * tiles_n;               // 256-row tiles
+  const int num_kb = (K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);                    // leader's: its own expect_tx arrival (+ bytes of both CTAs)
+      ptx::mbar_init(empty_bar(s), 1);                   // one multicast commit from the leader's MMA thread
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(tfull_bar(s), 1);                   // one multicast commit
+      ptx::mbar_init(tempty_bar(s), 2 * kEpiWarps);      // leader's: the epilogue warps of both CTAs
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();                               // peer barriers initialised before any remote signal
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  pdl_wait();
+  const bool skip = (p.skip_flag != nullptr && *p.skip_flag != 0);
+
+  if (skip) {
+    // fall through to the teardown
+  } else if (warp == 0) {
+    // ===================================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+        const int a_row = m_blk * (2 * kBM) + (int)rank * kBM;
+        const int b_row = n_blk * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (!bounded_wait(empty_bar(stage), phase ^ 1u, 1)) goto done;
+          const uint32_t lead_full = ptx::mapa_shared(full_bar(stage), 0);
+          if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+          ptx::tma_load_2d_pair(smem_a0 + stage * Cfg::kABytes, &tmap_a, kb * kBK, a_row, lead_full);
+          ptx::tma_load_2d_pair(smem_b0 + stage * Cfg::kBBytes, &tmap_w, kb * kBK, b_row, lead_full);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (leader CTA, one thread)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_pair<BN>();
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        if (!bounded_wait(tempty_bar(acc), acc_phase ^ 1u, 2)) goto done;
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (!bounded_wait(full_bar(stage), phase, 3)) goto done;
+          ptx::tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_a0 + stage * Cfg::kABytes);
+          const uint64_t bdesc = make_smem_desc(smem_b0 + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            ptx::umma_bf16_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                (kb > 0 || k > 0) ? 1u : 0u);
+          ptx::umma_commit_pair(empty_bar(stage), (uint16_t)3);     // frees the stage in both CTAs
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit_pair(tfull_bar(acc), (uint16_t)3);         // accumulator ready in both CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= kFirstEpiWarp) {
+    // ===================================================================== epilogue warps (both CTAs)
+    const int e = warp - kFirstEpiWarp;
+    const int quad = warp & 3;
+    const int half = e >> 2;
+    const uint32_t stg = smem_epi + (uint32_t)e * kEpiStageBytes;
+    int acc = 0; uint32_t acc_phase = 0;
+    int cur_len = 0;
+    if (EPI == EPI_ARGMAX) cur_len = (p.cur_len != nullptr) ? *p.cur_len : (1 << 30);
+    for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+      const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+      if (!bounded_wait(tfull_bar(acc), acc_phase, 4)) break;
+      ptx::tc_fence_after();
+      epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m_blk * (2 * kBM) + (int)rank * kBM + quad * 32, n_blk,
+                             quad, half, lane, stg, cur_len);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(tempty_bar(acc), 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    pdl_trigger_bottom();
+  }
+done:
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();          // the peer may still be read by the leader's MMAs / signalled by its commits
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
   }
 }
 

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, void* __restrict__ y,
                                                         long long ldy, int rows, int width,
                                                         const int* __restrict__ skip_flag) {
-  pdl_launch_dependents();
+  pdl_trigger_top();
   pdl_wait();
   if (skip_flag != nullptr && *skip_flag != 0) return;
   const int lane = threadIdx.x & 31;
@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
   float mean, rstd;
   ln_stats(v, nvec, lane, width, mean, rstd);
+  pdl_trigger_bottom();
   void* yrow = kBf16Out ? (void*)(reinterpret_cast<bf16*>(y) + (size_t)row * ldy)
                         : (void*)(reinterpret_cast<float*>(y) + (size_t)row * ldy);
   ln_store<kBf16Out>(v, nvec, lane, mean, rstd, gamma, beta, yrow);

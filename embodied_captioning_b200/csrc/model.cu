@@ -63,10 +63,12 @@ Model::Model(const ec_config& c, int dev) : cfg(c), device(dev) {
 Model::~Model() {
   cudaSetDevice(device);
   for (void* p : owned) cudaFree(p);
-  if (graph_exec) cudaGraphExecDestroy(graph_exec);
-  if (side_stream) cudaStreamDestroy(side_stream);
-  if (ev_in) cudaEventDestroy(ev_in);
-  if (ev_out) cudaEventDestroy(ev_out);
+  for (int c = 0; c < kMaxChains; ++c) {
+    if (graph_exec[c]) cudaGraphExecDestroy(graph_exec[c]);
+    if (chain_streams[c]) cudaStreamDestroy(chain_streams[c]);
+    if (chain_done[c]) cudaEventDestroy(chain_done[c]);
+  }
+  if (chain_fork) cudaEventDestroy(chain_fork);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -356,8 +358,24 @@ struct DecodeWs {
   bf16* ln_kv; bf16* cross_kv; bf16* tk; bf16* tv; bf16* dk; bf16* dv;
   float* x; bf16* ln; bf16* qkv; bf16* att; bf16* fc1; bf16* q;
   float* part_val; int* part_idx; unsigned char* finished; DecodeState* st; int* tokens_tf;
+  size_t cache_layer;    // elements between the self-K/V caches of consecutive layers (whole batch)
+  size_t cross_layer;    // elements between the cross-K/V caches of consecutive layers (whole batch)
   size_t bytes;
 };
+
+// rows [r0, ...) of every per-crop buffer: the view one decoder chain works on (layer strides stay global)
+static DecodeWs slice_rows(const Model& m, const DecodeWs& w, int r0, int seq_len, int chain) {
+  const ec_config& c = m.cfg;
+  const size_t T = c.text_width, NK = c.n_queries - 1, L = seq_len, r = (size_t)r0;
+  const size_t parts = (size_t)gemm_argmax_parts(c.vocab_size);
+  DecodeWs v = w;
+  v.ln_kv += r * NK * T; v.cross_kv += r * NK * 2 * T;
+  v.tk += r * L * T; v.tv += r * L * T; v.dk += r * L * T; v.dv += r * L * T;
+  v.x += r * T; v.ln += r * T; v.qkv += r * 3 * T; v.att += r * T; v.fc1 += r * 4 * T; v.q += r * T;
+  v.part_val += r * parts; v.part_idx += r * parts; v.finished += r; v.tokens_tf += r * L;
+  v.st += chain;
+  return v;
+}
 
 static DecodeWs carve_decode(const Model& m, void* ws, int n, int seq_len) {
   const ec_config& c = m.cfg;
@@ -381,8 +399,10 @@ static DecodeWs carve_decode(const Model& m, void* ws, int n, int seq_len) {
   w.part_val = b.take<float>((size_t)n * parts);
   w.part_idx = b.take<int>((size_t)n * parts);
   w.finished = b.take<unsigned char>((size_t)n);
-  w.st = b.take<DecodeState>(1);
+  w.st = b.take<DecodeState>(kMaxChains);
   w.tokens_tf = b.take<int>((size_t)n * L);
+  w.cache_layer = (size_t)n * L * T;
+  w.cross_layer = (size_t)n * NK * 2 * T;
   w.bytes = b.off;
   return w;
 }
@@ -418,22 +438,22 @@ int Model::cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int n,
   return EC_OK;
 }
 
-// one decoder step for all crops: token at position cur_len-1 in, token cur_len out
-int Model::decode_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int seq_len, int min_len, float* logits,
-                       bool teacher_forced, cudaStream_t s) {
-  const int T = cfg.text_width, NK = cfg.n_queries - 1, V = cfg.vocab_size;
-  const size_t cache_layer = (size_t)n * seq_len * T;
+// one decoder step for the crops of one chain (`w` is the chain's row view): token at position cur_len-1 in,
+// token cur_len out.  Chains only share the read-only step state and the `next_active` counter.
+int Model::chain_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len,
+                      float* logits, bool teacher_forced, cudaStream_t s) {
+  const int T = cfg.text_width, V = cfg.vocab_size;
   EC_TRY(decode_embed(tokens, ld_tokens, tok_emb, txt_pos, w.x, n, T, w.st, s));
   for (int l = 0; l < cfg.text_layers; ++l)
-    EC_TRY(self_block(tblocks[l], w, w.tk + l * cache_layer, w.tv + l * cache_layer, n, seq_len, cfg.text_heads, s));
+    EC_TRY(self_block(tblocks[l], w, w.tk + l * w.cache_layer, w.tv + l * w.cache_layer, n, seq_len, cfg.text_heads, s));
   for (int l = 0; l < cfg.mm_layers; ++l) {
-    EC_TRY(self_block(dself[l], w, w.dk + l * cache_layer, w.dv + l * cache_layer, n, seq_len, cfg.mm_heads, s));
-    EC_TRY(cross_block(dcross[l], w, w.cross_kv + (size_t)l * n * NK * 2 * T, n, s));
+    EC_TRY(self_block(dself[l], w, w.dk + l * w.cache_layer, w.dv + l * w.cache_layer, n, seq_len, cfg.mm_heads, s));
+    EC_TRY(cross_block(dcross[l], w, w.cross_kv + l * w.cross_layer, n, s));
   }
   EC_TRY(layernorm(w.x, T, ln_final_g, ln_final_b, w.ln, T, true, n, T, &w.st->done, s));
   GemmArgs g{};
   g.A = w.ln; g.lda = T; g.W = w_vocab; g.ldw = T; g.M = n; g.N = V; g.K = T;
-  g.logits = logits; g.ld_logits = V; g.logits_step_stride = (long long)n * V;
+  g.logits = logits; g.ld_logits = V; g.logits_step_stride = (long long)n_total * V;
   g.part_val = w.part_val; g.part_idx = w.part_idx; g.n_parts = gemm_argmax_parts(V);
   g.eos_col = teacher_forced ? -1 : cfg.eos_token_id; g.cur_len = &w.st->cur_len; g.min_len = min_len;
   g.skip_flag = &w.st->done;
@@ -441,8 +461,29 @@ int Model::decode_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int
   if (!teacher_forced)
     EC_TRY(decode_select(w.part_val, w.part_idx, g.n_parts, tokens, ld_tokens, w.finished, n, seq_len,
                          cfg.eos_token_id, cfg.pad_token_id, w.st, s));
-  EC_TRY(decode_advance(w.st, teacher_forced, n, s));
   return EC_OK;
+}
+
+// Rows per chain.  At a batch of ~1000 crops every kernel of the step except the cross-attention stream is
+// latency-bound (a [1024 x 768] GEMM occupies two thirds of the SMs for ~6 us, most of it launch + pipeline fill),
+// so the batch is cut into independent row chains.  Each chain owns a stream, a device-resident DecodeState and a
+// LINEAR captured step graph that is replayed on that stream: measured on B200, parallel branches inside one graph
+// double the dependent-kernel latency (12.6 vs 6.3 us per level) whereas separate linear graphs on separate streams
+// overlap almost perfectly (8 chains: 7.9 us per level).  The small kernels of one chain fill the SMs the others
+// leave idle and ride underneath the HBM-bound cross-K/V stream of another chain.
+int Model::chain_rows(int n) const {
+  static const int env_chains = [] { const char* e = getenv("EC_DECODE_CHAINS"); return e ? atoi(e) : 0; }();
+  int nc = decode_chains > 0 ? decode_chains : env_chains;
+  if (nc <= 0) nc = ceil_div(n, 128);
+  nc = std::max(1, std::min(nc, kMaxChains));
+  const int per = ceil_div(ceil_div(n, nc), 128) * 128;     // whole GEMM row tiles per chain
+  return std::max(per, 1);
+}
+
+int Model::decode_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len,
+                       float* logits, bool teacher_forced, cudaStream_t s) {
+  EC_TRY(chain_step(w, tokens, ld_tokens, n, n_total, seq_len, min_len, logits, teacher_forced, s));
+  return decode_advance(w.st, teacher_forced, n, s);
 }
 
 int Model::prefill_cross_kv(const DecodeWs& w, const float* embs, int n, cudaStream_t s) {
@@ -457,43 +498,68 @@ int Model::prefill_cross_kv(const DecodeWs& w, const float* embs, int n, cudaStr
   return EC_OK;
 }
 
-int Model::run_steps(const DecodeWs& w, int* tokens, int ld_tokens, int n, int seq_len, int min_len, float* logits,
-                     bool teacher_forced, int steps, cudaStream_t s) {
+// `steps` decoder steps of one chain on its own stream `cs` (graph replay or eager launches)
+int Model::run_chain(int c, const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len,
+                     float* logits, bool teacher_forced, int steps, cudaStream_t cs) {
   if (!use_graph) {
-    for (int t = 0; t < steps; ++t) EC_TRY(decode_step(w, tokens, ld_tokens, n, seq_len, min_len, logits, teacher_forced, s));
+    for (int t = 0; t < steps; ++t)
+      EC_TRY(decode_step(w, tokens, ld_tokens, n, n_total, seq_len, min_len, logits, teacher_forced, cs));
     return EC_OK;
   }
-  // CUDA-graph path: capture one step on a private stream (the caller's stream may be the legacy default
-  // stream, which cannot be captured), replay it `steps` times; re-capture only when the launch set changes.
-  if (!side_stream) {
-    EC_CHECK_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
-    EC_CHECK_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
-    EC_CHECK_CUDA(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
-  }
-  GraphKey key{w.x, tokens, logits, n, seq_len, min_len, ld_tokens, teacher_forced ? 1 : 0};
-  if (!graph_exec || memcmp(&key, &graph_key, sizeof(GraphKey)) != 0) {
-    if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+  // capture one step on the chain's private stream, replay it `steps` times; re-capture only when the launch set changes
+  GraphKey key{w.x, tokens, logits, n, seq_len, min_len, ld_tokens, teacher_forced ? 1 : 0, n_total};
+  if (!graph_exec[c] || memcmp(&key, &graph_key[c], sizeof(GraphKey)) != 0) {
+    if (graph_exec[c]) { cudaGraphExecDestroy(graph_exec[c]); graph_exec[c] = nullptr; }
     cudaGraph_t graph = nullptr;
-    EC_CHECK_CUDA(cudaStreamBeginCapture(side_stream, cudaStreamCaptureModeThreadLocal));
+    EC_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
     const long long before = launch_count();
-    int rc = decode_step(w, tokens, ld_tokens, n, seq_len, min_len, logits, teacher_forced, side_stream);
-    graph_nodes = launch_count() - before;
-    note_launches(-graph_nodes);                      // captured, not launched
-    cudaError_t ce = cudaStreamEndCapture(side_stream, &graph);
+    int rc = decode_step(w, tokens, ld_tokens, n, n_total, seq_len, min_len, logits, teacher_forced, cs);
+    graph_nodes[c] = launch_count() - before;
+    note_launches(-graph_nodes[c]);                      // captured, not launched
+    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
     if (rc != EC_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     EC_CHECK_CUDA(ce);
-    ce = cudaGraphInstantiate(&graph_exec, graph, 0);
+    ce = cudaGraphInstantiate(&graph_exec[c], graph, 0);
     cudaGraphDestroy(graph);
     EC_CHECK_CUDA(ce);
-    graph_key = key;
+    graph_key[c] = key;
   }
-  EC_CHECK_CUDA(cudaEventRecord(ev_in, s));
-  EC_CHECK_CUDA(cudaStreamWaitEvent(side_stream, ev_in, 0));
-  for (int t = 0; t < steps; ++t) EC_CHECK_CUDA(cudaGraphLaunch(graph_exec, side_stream));
-  note_launches(graph_nodes * steps);
-  EC_CHECK_CUDA(cudaEventRecord(ev_out, side_stream));
-  EC_CHECK_CUDA(cudaStreamWaitEvent(s, ev_out, 0));
+  for (int t = 0; t < steps; ++t) EC_CHECK_CUDA(cudaGraphLaunch(graph_exec[c], cs));
+  note_launches(graph_nodes[c] * steps);
   return EC_OK;
+}
+
+// fork the caller's stream into the row chains, run `steps` steps on each, join
+int Model::run_steps(const DecodeWs& w, int* tokens, int ld_tokens, int n, int seq_len, int min_len, float* logits,
+                     bool teacher_forced, int steps, cudaStream_t s) {
+  if (chain_fork == nullptr) {
+    for (int c = 0; c < kMaxChains; ++c) {
+      EC_CHECK_CUDA(cudaStreamCreateWithFlags(&chain_streams[c], cudaStreamNonBlocking));
+      EC_CHECK_CUDA(cudaEventCreateWithFlags(&chain_done[c], cudaEventDisableTiming));
+    }
+    EC_CHECK_CUDA(cudaEventCreateWithFlags(&chain_fork, cudaEventDisableTiming));
+  }
+  const int per = chain_rows(n);
+  const int nc = ceil_div(n, per);
+  // step state of every chain (stream-ordered before the fork)
+  for (int c = 0; c < nc; ++c) {
+    const int r0 = c * per, nr = std::min(per, n - r0);
+    EC_TRY(decode_init(teacher_forced ? nullptr : tokens + (size_t)r0 * ld_tokens, ld_tokens, w.finished + r0, nr, seq_len,
+                       cfg.sot_token_id, cfg.pad_token_id, w.st + c, s));
+  }
+  EC_CHECK_CUDA(cudaEventRecord(chain_fork, s));
+  int rc = EC_OK;
+  for (int c = 0; c < nc && rc == EC_OK; ++c) {
+    const int r0 = c * per, nr = std::min(per, n - r0);
+    cudaStream_t cs = chain_streams[c];
+    EC_CHECK_CUDA(cudaStreamWaitEvent(cs, chain_fork, 0));
+    const DecodeWs v = slice_rows(*this, w, r0, seq_len, c);
+    rc = run_chain(c, v, tokens + (size_t)r0 * ld_tokens, ld_tokens, nr, n, seq_len, min_len,
+                   logits ? logits + (size_t)r0 * cfg.vocab_size : nullptr, teacher_forced, steps, cs);
+    EC_CHECK_CUDA(cudaEventRecord(chain_done[c], cs));
+    EC_CHECK_CUDA(cudaStreamWaitEvent(s, chain_done[c], 0));
+  }
+  return rc;
 }
 
 int Model::decode_greedy(const float* embs, int n, int seq_len, int min_len, int* tokens, float* logits, void* ws,
@@ -507,7 +573,6 @@ int Model::decode_greedy(const float* embs, int n, int seq_len, int min_len, int
   const DecodeWs w = carve_decode(*this, ws, n, seq_len);
   EC_REQUIRE(ws_bytes >= w.bytes, EC_ERR_WORKSPACE, "decode workspace %zu < %zu", ws_bytes, w.bytes);
   EC_TRY(prefill_cross_kv(w, embs, n, s));
-  EC_TRY(decode_init(tokens, seq_len, w.finished, n, seq_len, cfg.sot_token_id, cfg.pad_token_id, w.st, s));
   return run_steps(w, tokens, seq_len, n, seq_len, min_len, logits, false, seq_len - 1, s);
 }
 
@@ -522,7 +587,7 @@ int Model::forward_logits(const float* embs, const int* text, int n, int t, floa
   EC_REQUIRE(ws_bytes >= w.bytes, EC_ERR_WORKSPACE, "decode workspace %zu < %zu", ws_bytes, w.bytes);
   EC_TRY(prefill_cross_kv(w, embs, n, s));
   // teacher forcing: the step engine reads its input token from a [n, L] table holding the given text
-  EC_TRY(decode_init(w.tokens_tf, L, w.finished, n, L, cfg.sot_token_id, cfg.pad_token_id, w.st, s));
+  EC_CHECK_CUDA(cudaMemsetAsync(w.tokens_tf, 0, (size_t)n * L * sizeof(int), s));
   EC_CHECK_CUDA(cudaMemcpy2DAsync(w.tokens_tf, (size_t)L * sizeof(int), text, (size_t)t * sizeof(int),
                                   (size_t)t * sizeof(int), n, cudaMemcpyDeviceToDevice, s));
   return run_steps(w, w.tokens_tf, L, n, L, 0, logits, true, t, s);

@@ -16,7 +16,9 @@ struct Block {   // one open_clip ResidualAttentionBlock
 
 struct DecodeWs;
 
-struct GraphKey { const void* ws; const void* tokens; const void* logits; int n, seq_len, min_len, ld, tf; };
+struct GraphKey { const void* ws; const void* tokens; const void* logits; int n, seq_len, min_len, ld, tf, n_total; };
+
+constexpr int kMaxChains = 8;
 
 struct Model {
   ec_config cfg;
@@ -44,11 +46,14 @@ struct Model {
 
   std::vector<void*> owned;
   // CUDA-graph replay of the decoder step
-  cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-  cudaGraphExec_t graph_exec = nullptr;
-  GraphKey graph_key{};
-  long long graph_nodes = 0;
+  // decoder row chains: each owns a stream and a linear step graph; 0 = choose from the batch size
+  int decode_chains = 0;
+  cudaStream_t chain_streams[kMaxChains] = {};
+  cudaEvent_t chain_done[kMaxChains] = {};
+  cudaEvent_t chain_fork = nullptr;
+  cudaGraphExec_t graph_exec[kMaxChains] = {};
+  GraphKey graph_key[kMaxChains] = {};
+  long long graph_nodes[kMaxChains] = {};
 
   Model(const ec_config& c, int dev);
   ~Model();
@@ -73,8 +78,13 @@ struct Model {
   int set_block_tensor(Block& b, int width, const char* leaf, const char* name, const float* h, int64_t numel);
   int self_block(const Block& b, const DecodeWs& w, bf16* kc, bf16* vc, int n, int max_len, int heads, cudaStream_t s);
   int cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int n, cudaStream_t s);
-  int decode_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int seq_len, int min_len, float* logits,
-                  bool teacher_forced, cudaStream_t s);
+  int chain_rows(int n) const;
+  int chain_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len,
+                 float* logits, bool teacher_forced, cudaStream_t s);
+  int decode_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len,
+                  float* logits, bool teacher_forced, cudaStream_t s);
+  int run_chain(int c, const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len,
+                float* logits, bool teacher_forced, int steps, cudaStream_t cs);
   int prefill_cross_kv(const DecodeWs& w, const float* embs, int n, cudaStream_t s);
   int run_steps(const DecodeWs& w, int* tokens, int ld_tokens, int n, int seq_len, int min_len, float* logits,
                 bool teacher_forced, int steps, cudaStream_t s);

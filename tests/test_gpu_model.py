@@ -150,6 +150,35 @@ def test_cuda_graph_decode_is_identical(tiny, device):
     assert torch.equal(a, b) and torch.equal(a, c)
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_decoder_row_chains_are_bit_identical(device, graph):
+    """The decoder step cut into 1 / 2 / 3 / 4 independent row chains (forked streams or graph branches) must give
+    bit-identical tokens AND logits: rows never interact, so chaining may only change scheduling."""
+    cfg = get_config("coca_tiny")
+    sd = synth.make_state_dict(cfg, seed=1234)
+    model = CoCa(cfg, device=device)
+    model.load_state_dict(sd)
+    model.set_decode_graph(graph)
+    n = 300                                            # not a multiple of the 128-row GEMM tile
+    g = torch.Generator().manual_seed(5)
+    embs = torch.randn((n, cfg.n_image_embs, cfg.embed_dim), generator=g).to(device)
+    outs = []
+    for chains in (1, 2, 3, 4):
+        model.set_decode_chains(chains)
+        o = model.generate(None, image_embs=embs, generation_type="top_k", seq_len=9, fixed_output_length=True)
+        outs.append((o["text"].clone(), torch.stack([l for l in o["logits"]]).clone()))
+    ops.check_watchdog(device)
+    for tok, lg in outs[1:]:
+        assert torch.equal(tok, outs[0][0])
+        assert torch.equal(lg, outs[0][1])
+    text = outs[0][0][:, :6]
+    model.set_decode_chains(1)
+    a = model.forward(None, text, image_latent=torch.zeros(n, cfg.embed_dim), image_embs=embs, output_labels=False)["logits"]
+    model.set_decode_chains(4)
+    b = model.forward(None, text, image_latent=torch.zeros(n, cfg.embed_dim), image_embs=embs, output_labels=False)["logits"]
+    assert torch.equal(a, b)
+
+
 def test_early_eos_and_padding_protocol(device):
     """Make EOS the arg-max so rows stop at the first allowed position: checks min-length masking, PAD after
     EOS, early loop exit (output shorter than seq_len) and the ragged logits list."""
