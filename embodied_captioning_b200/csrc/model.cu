@@ -464,17 +464,18 @@ int Model::chain_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int 
   return EC_OK;
 }
 
-// Rows per chain.  At a batch of ~1000 crops every kernel of the step except the cross-attention stream is
-// latency-bound (a [1024 x 768] GEMM occupies two thirds of the SMs for ~6 us, most of it launch + pipeline fill),
-// so the batch is cut into independent row chains.  Each chain owns a stream, a device-resident DecodeState and a
-// LINEAR captured step graph that is replayed on that stream: measured on B200, parallel branches inside one graph
-// double the dependent-kernel latency (12.6 vs 6.3 us per level) whereas separate linear graphs on separate streams
-// overlap almost perfectly (8 chains: 7.9 us per level).  The small kernels of one chain fill the SMs the others
-// leave idle and ride underneath the HBM-bound cross-K/V stream of another chain.
+// Rows per chain.  The batch can be cut into independent row chains; each chain owns a stream, a device-resident
+// DecodeState and a LINEAR captured step graph replayed on that stream (measured on B200: parallel branches inside
+// one graph double the dependent-kernel latency, 12.6 vs 6.3 us per level, whereas separate linear graphs on
+// separate streams overlap almost perfectly).  Measured result for this decoder (profiles/r01_decoder_chains.txt):
+// the step is a chain of ~250 DEPENDENT kernels whose individual latency (~10 us per GEMM level, set by each CTA
+// streaming its own K panel at ~85 GB/s per SM) does not shrink with fewer rows, so chaining neither helps nor
+// hurts at 1024 crops (122 ms with 1 chain, 125 ms with 8).  Default: one chain; the option stays for larger
+// batches, where several chains share one latency chain.
 int Model::chain_rows(int n) const {
   static const int env_chains = [] { const char* e = getenv("EC_DECODE_CHAINS"); return e ? atoi(e) : 0; }();
   int nc = decode_chains > 0 ? decode_chains : env_chains;
-  if (nc <= 0) nc = ceil_div(n, 128);
+  if (nc <= 0) nc = 1;
   nc = std::max(1, std::min(nc, kMaxChains));
   const int per = ceil_div(ceil_div(n, nc), 128) * 128;     // whole GEMM row tiles per chain
   return std::max(per, 1);
