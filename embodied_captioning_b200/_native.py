@@ -24,6 +24,8 @@ EXPORTS = [
     "ec_disagreement_workspace_bytes", "ec_instance_disagreement", "ec_instance_disagreement_peers",
     "ec_gemm_bf16", "ec_gemm_argmax", "ec_layernorm", "ec_attention", "ec_check_watchdog",
     "ec_launch_count", "ec_profile_gemm", "ec_profile_gemm_read", "ec_attention_fused_qkv",
+    "ec_disagreement_map_workspace_bytes", "ec_disagreement_map",
+    "ec_caption_frequency_workspace_bytes", "ec_caption_frequency",
 ]
 
 
@@ -81,6 +83,12 @@ def lib() -> C.CDLL:
     L.ec_attention.argtypes = [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64, i32, i32, i32, i32, i32, vp]
     L.ec_check_watchdog.argtypes = [vp]
     L.ec_attention_fused_qkv.argtypes = [vp, i64, i32, i32, i32, vp, i64, i64, i32, i32, i32, i32, i32, vp]
+    L.ec_disagreement_map_workspace_bytes.argtypes = [i32, i32, i32]
+    L.ec_disagreement_map_workspace_bytes.restype = sz
+    L.ec_disagreement_map.argtypes = [vp, i32, vp, vp, vp, i32, C.c_float, i32, i32, i32, i32, vp, vp, vp, sz, vp]
+    L.ec_caption_frequency_workspace_bytes.argtypes = [i32]
+    L.ec_caption_frequency_workspace_bytes.restype = sz
+    L.ec_caption_frequency.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp, vp, vp, sz, vp]
     L.ec_launch_count.argtypes = []
     L.ec_launch_count.restype = C.c_int64
     L.ec_profile_gemm.argtypes = [i32]

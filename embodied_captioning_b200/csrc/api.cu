@@ -131,6 +131,33 @@ int ec_instance_disagreement_peers(const float* const* peers, int32_t world, int
                                      out_count, out_m, ws, ws_bytes, as_stream(stream));
 }
 
+size_t ec_caption_frequency_workspace_bytes(int32_t n) { return caption_frequency_workspace_bytes(n); }
+
+int ec_caption_frequency(const int32_t* tokens, int32_t ld_tokens, int32_t t, const int64_t* keys, int32_t n,
+                         int64_t* out_key, int32_t* out_first, int32_t* out_count, int32_t* out_m, void* ws,
+                         size_t ws_bytes, void* stream) {
+  EC_REQUIRE(out_key && out_first && out_count && out_m, EC_ERR_INVALID, "ec_caption_frequency: null output");
+  EC_REQUIRE(n == 0 || (tokens && keys && ws), EC_ERR_INVALID, "ec_caption_frequency: null input");
+  return caption_frequency(tokens, ld_tokens, t, reinterpret_cast<const long long*>(keys), n,
+                           reinterpret_cast<long long*>(out_key), out_first, out_count, out_m, ws, ws_bytes,
+                           as_stream(stream));
+}
+
+size_t ec_disagreement_map_workspace_bytes(int32_t n_points, int32_t h, int32_t w) {
+  return disagreement_map_workspace_bytes(n_points, h, w);
+}
+
+int ec_disagreement_map(const float* points, int32_t n_points, const int64_t* point_keys, const int64_t* inst_keys,
+                        const float* inst_scores, int32_t m, float scale, int32_t off_x, int32_t off_y, int32_t h,
+                        int32_t w, float* map, float* reward, void* ws, size_t ws_bytes, void* stream) {
+  EC_REQUIRE(map && ws, EC_ERR_INVALID, "ec_disagreement_map: null output");
+  EC_REQUIRE(n_points == 0 || (points && point_keys), EC_ERR_INVALID, "ec_disagreement_map: null points");
+  EC_REQUIRE(m == 0 || (inst_keys && inst_scores), EC_ERR_INVALID, "ec_disagreement_map: null instance table");
+  return disagreement_map(points, n_points, reinterpret_cast<const long long*>(point_keys),
+                          reinterpret_cast<const long long*>(inst_keys), inst_scores, m, scale, off_x, off_y, h, w, map,
+                          reward, ws, ws_bytes, as_stream(stream));
+}
+
 int ec_gemm_bf16(const void* a, int32_t lda, const void* w, int32_t ldw, int32_t m, int32_t n, int32_t k,
                  const float* bias, const float* residual, int32_t ldr, void* out, int32_t ldo, int32_t epilogue,
                  int32_t use_simt_reference, void* stream) {

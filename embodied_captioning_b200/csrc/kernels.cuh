@@ -94,4 +94,20 @@ int instance_disagreement_peers(const float* const* peers_dev, int world, int ro
                                 long long* out_keys, float* out_score, int* out_count, int* out_m, void* ws,
                                 size_t ws_bytes, cudaStream_t stream);
 
+// Caption frequency table (pseudocaptioner.py:156-177) over token-id rows: one output entry per distinct
+// (instance key, caption): the key, the row index of its FIRST occurrence and how many rows share it; entries are
+// ordered by (key, first occurrence), i.e. dict insertion order inside every instance.  Synchronises the stream.
+size_t caption_frequency_workspace_bytes(int n);
+int caption_frequency(const int* tokens, int ld_tokens, int t, const long long* keys, int n, long long* out_key,
+                      int* out_first, int* out_count, int* out_m, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+// ---- rasterize.cu -----------------------------------------------------------------------------------
+// Disagreement map + reward (projection_utils.py:694-703,760-785; env_habitat3.py:75-84).  points f32 [P,3]
+// (x, y, z: x -> column, z -> row), point_keys int64 [P] = object id of each point, (inst_keys, inst_scores) =
+// key-sorted output of instance_disagreement.  map f32 [H,W] is fully overwritten; reward (nullable) = sum/1000.
+size_t disagreement_map_workspace_bytes(int n_points, int H, int W);
+int disagreement_map(const float* points, int n_points, const long long* point_keys, const long long* inst_keys,
+                     const float* inst_scores, int m, float scale, int off_x, int off_y, int H, int W, float* map,
+                     float* reward, void* ws, size_t ws_bytes, cudaStream_t stream);
+
 }  // namespace ec

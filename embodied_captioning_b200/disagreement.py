@@ -85,9 +85,51 @@ def pandas_group_order(keys: np.ndarray) -> np.ndarray:
     return np.array(sorted(range(len(labels)), key=lambda i: labels[i]), dtype=np.int64)
 
 
-def instance_disagreement(emb: torch.Tensor, keys: torch.Tensor, mode: int = MODE_FULL_MEAN_1MINUS):
-    """emb [N,D] f32, keys [N] int64 (device tensors) -> (keys[M], score[M], count[M]) sorted by key."""
-    return ops.instance_disagreement(emb.contiguous(), keys.contiguous(), mode)
+def instance_disagreement(emb: torch.Tensor, keys: torch.Tensor, mode: int = MODE_FULL_MEAN_1MINUS,
+                          dedup: bool = False):
+    """emb [N,D] f32, keys [N] int64 (device tensors) -> (keys[M], score[M], count[M]) sorted by key.
+    dedup=True applies the world model's `unique(dim=0)` per instance first (projection_utils.py:574-578)."""
+    return ops.instance_disagreement(emb.contiguous(), keys.contiguous(), mode, dedup)
+
+
+def map_geometry(lower_bound, upper_bound, map_scale: float = 0.025):
+    """Grid size and integer origin of the top-down map (projection_utils.py:683-699) -> (H, W, off_x, off_y)."""
+    H = int(abs(upper_bound[2] - lower_bound[2]) / map_scale)
+    W = int(abs(upper_bound[0] - lower_bound[0]) / map_scale)
+    return H, W, int(np.floor(lower_bound[0] / map_scale)), int(np.ceil(lower_bound[2] / map_scale))
+
+
+def disagreement_map(points: torch.Tensor, point_keys: torch.Tensor, inst_keys: torch.Tensor,
+                     inst_scores: torch.Tensor, lower_bound, upper_bound, map_scale: float = 0.025):
+    """Top-down disagreement map + exploration reward on the device.
+
+    Replaces the score gather / centre write / six inflate writes of `get_topdown_semantic`
+    (projection_utils.py:760-785) and `get_reward` (env_habitat3.py:75-84).  points f32 [P,3], point_keys int64 [P]
+    (object id of every 3-D point), (inst_keys, inst_scores) the key-sorted result of `instance_disagreement`.
+    Returns (map f32 [H,W], reward 0-d f32 tensor), both on the device."""
+    from . import _native as nat
+    H, W, off_x, off_y = map_geometry(lower_bound, upper_bound, map_scale)
+    if H <= 0 or W <= 0:
+        raise ValueError("empty map bounds")
+    dev = points.device
+    if not points.is_cuda:
+        raise nat.NativeError("expected CUDA tensors (there is no CPU path)")
+    pts = points.to(torch.float32).contiguous()
+    pk = point_keys.to(torch.int64).contiguous()
+    ik = inst_keys.to(torch.int64).contiguous()
+    isc = inst_scores.to(torch.float32).contiguous()
+    P, M = pts.shape[0], ik.shape[0]
+    out = torch.empty((H, W), device=dev, dtype=torch.float32)
+    reward = torch.zeros((), device=dev, dtype=torch.float32)
+    lib = nat.lib()
+    ws = torch.empty((lib.ec_disagreement_map_workspace_bytes(P, H, W),), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        nat.check(lib.ec_disagreement_map(nat.ptr(pts) if P else None, P, nat.ptr(pk) if P else None,
+                                          nat.ptr(ik) if M else None, nat.ptr(isc) if M else None, M,
+                                          float(np.float32(map_scale)), off_x, off_y, H, W, out.data_ptr(),
+                                          reward.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          torch.cuda.current_stream(dev).cuda_stream), "ec_disagreement_map")
+    return out, reward
 
 
 def group_mean(scores: torch.Tensor) -> float:

@@ -13,6 +13,7 @@ from . import _native as nat
 
 EPI_BF16, EPI_BF16_GELU, EPI_F32, EPI_F32_RESID = 0, 1, 2, 3
 MODE_FULL_MEAN_1MINUS, MODE_PAIRS_MEAN_COS = 0, 1
+DEDUP = 4            # EC_DISAGREEMENT_DEDUP: OR into the mode (projection_utils.py:574-578 `unique(dim=0)`)
 
 
 def _stream(t: torch.Tensor) -> int:
@@ -126,8 +127,10 @@ def preprocess_crops(frames: torch.Tensor, rects: torch.Tensor, frame_idx: torch
     return out_bf16, out_f32, status[:N]
 
 
-def instance_disagreement(emb: torch.Tensor, keys: torch.Tensor, mode: int = MODE_FULL_MEAN_1MINUS):
-    """emb f32 [N,D], keys int64 [N] on device -> (keys[M] int64, score[M] f32, count[M] int32), key-sorted."""
+def instance_disagreement(emb: torch.Tensor, keys: torch.Tensor, mode: int = MODE_FULL_MEAN_1MINUS, dedup: bool = False):
+    """emb f32 [N,D], keys int64 [N] on device -> (keys[M] int64, score[M] f32, count[M] int32), key-sorted.
+    dedup=True removes exact-duplicate views of an instance first (count = distinct views)."""
+    mode = int(mode) | (DEDUP if dedup else 0)
     _check_dev(emb, keys)
     assert emb.dtype == torch.float32 and emb.dim() == 2 and emb.stride(1) == 1
     assert keys.dtype == torch.int64 and keys.is_contiguous()
@@ -152,3 +155,26 @@ def instance_disagreement(emb: torch.Tensor, keys: torch.Tensor, mode: int = MOD
 def check_watchdog(device=None):
     with torch.cuda.device(device):
         nat.check(nat.lib().ec_check_watchdog(torch.cuda.current_stream(device).cuda_stream), "ec_check_watchdog")
+
+
+def caption_frequency(tokens: torch.Tensor, keys: torch.Tensor):
+    """tokens int [N,T], keys int64 [N] on device -> (key[M] int64, first_row[M] int32, count[M] int32): one entry per
+    distinct (instance, caption), ordered by (key, first occurrence) -- `compute_captions_frequency`
+    (pseudocaptioner.py:156-177) on token rows."""
+    _check_dev(tokens, keys)
+    tok = tokens.to(torch.int32).contiguous()
+    k = keys.to(torch.int64).contiguous()
+    N, T = tok.shape
+    dev = tok.device
+    ok = torch.empty((max(N, 1),), device=dev, dtype=torch.int64)
+    of = torch.empty((max(N, 1),), device=dev, dtype=torch.int32)
+    oc = torch.empty((max(N, 1),), device=dev, dtype=torch.int32)
+    m = torch.zeros((1,), device=dev, dtype=torch.int32)
+    lib = nat.lib()
+    ws = torch.empty((max(lib.ec_caption_frequency_workspace_bytes(N), 16),), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        nat.check(lib.ec_caption_frequency(tok.data_ptr() if N else None, tok.stride(0) if N else T, T,
+                                           k.data_ptr() if N else None, N, ok.data_ptr(), of.data_ptr(), oc.data_ptr(),
+                                           m.data_ptr(), ws.data_ptr(), ws.numel(), _stream(tok)), "ec_caption_frequency")
+    M = int(m.item())
+    return ok[:M], of[:M], oc[:M]

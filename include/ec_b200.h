@@ -88,6 +88,10 @@ int ec_forward_logits(ec_model* m, const float* embs_dev, const int32_t* text_de
 /* ---- per-instance disagreement: replaces the dict-comprehension over `_cosine_distance`
  * (projection_utils.py:743-754, 928-942; mode 0) and `mean_cosine_similarity`
  * (scripts/compute_cosine_sim.py:11-22; mode 1) grouped by instance key (pseudocaptioner.py:137). */
+/* OR-ed into `mode`: drop exact-duplicate view rows of an instance first, i.e. the `unique(dim=0)` that
+ * SemanticPointCloud.preprocess applies to every object's embedding set (projection_utils.py:574-578);
+ * out_count then holds the number of DISTINCT views.  Local rows only (not the peer-memory form). */
+#define EC_DISAGREEMENT_DEDUP 4
 size_t ec_disagreement_workspace_bytes(int32_t n);
 int ec_instance_disagreement(const float* emb_dev, int64_t ld_emb, const int64_t* keys_dev, int32_t n, int32_t d,
                              int32_t mode, int64_t* out_keys_dev, float* out_score_dev, int32_t* out_count_dev,
@@ -99,6 +103,28 @@ int ec_instance_disagreement_peers(const float* const* peers_dev, int32_t world,
                                    int32_t part_rank, int32_t part_world, int64_t* out_keys_dev,
                                    float* out_score_dev, int32_t* out_count_dev, int32_t* out_m_dev, void* ws_dev,
                                    size_t ws_bytes, void* stream);
+
+/* ---- caption frequency table per instance: replaces `PseudoCaptioner.compute_captions_frequency`
+ * (captioner/pseudocaptioner.py:156-177; grouping key :137) on token-id rows.  tokens int32 [n, ld] (first t columns
+ * compared), keys int64 [n].  One entry per distinct (key, caption): out_key, out_first (row of its first occurrence),
+ * out_count; ordered by (key, first occurrence) = dict insertion order inside an instance.  Synchronises `stream`. */
+size_t ec_caption_frequency_workspace_bytes(int32_t n);
+int ec_caption_frequency(const int32_t* tokens_dev, int32_t ld_tokens, int32_t t, const int64_t* keys_dev, int32_t n,
+                         int64_t* out_key_dev, int32_t* out_first_dev, int32_t* out_count_dev, int32_t* out_m_dev,
+                         void* ws_dev, size_t ws_bytes, void* stream);
+
+/* ---- disagreement map + exploration reward: replaces the score gather / centre write / six "inflate" writes of
+ * `SemanticPointCloud.get_topdown_semantic` (projection_utils.py:694-703,760-785) and `get_reward`
+ * (envs/env_habitat3.py:75-84).  points f32 [P,3] (x -> column, z -> row), point_keys int64 [P] (object id per
+ * point), inst_keys/inst_scores [m] = key-sorted output of ec_instance_disagreement.  off_x = floor(lower_x/scale),
+ * off_y = ceil(lower_z/scale) (host integers, projection_utils.py:694-699).  map f32 [h,w] is fully overwritten with
+ * numpy-assignment semantics (last write wins, negative indices wrap, an assignment with any out-of-range index is
+ * dropped whole); reward_dev (nullable) = map.sum() / 1000. */
+size_t ec_disagreement_map_workspace_bytes(int32_t n_points, int32_t h, int32_t w);
+int ec_disagreement_map(const float* points_dev, int32_t n_points, const int64_t* point_keys_dev,
+                        const int64_t* inst_keys_dev, const float* inst_scores_dev, int32_t m, float scale,
+                        int32_t off_x, int32_t off_y, int32_t h, int32_t w, float* map_dev, float* reward_dev,
+                        void* ws_dev, size_t ws_bytes, void* stream);
 
 /* ---- building blocks exported for unit tests and micro-benchmarks (same kernels the model path launches) */
 int ec_gemm_bf16(const void* a_bf16_dev, int32_t lda, const void* w_bf16_dev, int32_t ldw, int32_t m, int32_t n,

@@ -75,3 +75,72 @@ def test_reference_named_functions(device):
             return e[:len(caps)]
     dis.set_encoder(Enc())
     assert abs(dis.mean_cosine_similarity(["a", "b", "c"]) - do.mean_cosine_similarity_embeddings(e[:3])) < TOL
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_duplicate_view_removal_matches_unique_dim0(device, mode):
+    """`unique(dim=0)` of SemanticPointCloud.preprocess (projection_utils.py:574-578): exact-duplicate views of an
+    instance are dropped before the reduction; counts are the numbers of DISTINCT views (bit-exact)."""
+    rng = np.random.default_rng(17)
+    n, d, m = 3000, 384, 40
+    inst = rng.integers(0, m, size=n)
+    base = rng.normal(size=(200, d)).astype(np.float32)          # only 200 distinct rows -> many exact duplicates
+    emb = base[rng.integers(0, 200, size=n)].copy()
+    emb[5] = 0.0; emb[6] = -0.0; inst[5] = inst[6] = 3            # -0.0 == 0.0 for torch.unique
+    emb[7, 0] = 1e-30
+    keys = inst.astype(np.int64) * 1000003
+    k, s, c = ops.instance_disagreement(torch.from_numpy(emb).to(device), torch.from_numpy(keys).to(device), mode,
+                                        dedup=True)
+    # zero rows have no direction (0/0): keep them out of the score comparison but inside the count comparison
+    rk, rs, rc = do.instance_disagreement(emb, keys, mode="full" if mode == 0 else "pairs", dedup=True)
+    assert k.cpu().tolist() == rk.tolist()
+    assert c.cpu().tolist() == rc.tolist()
+    assert int(c.sum()) < n
+    got = s.cpu().numpy().astype(np.float64)
+    ok = ~np.isnan(rs) & ~np.isnan(got) & (rk != 3 * 1000003)
+    assert ok.sum() >= m - 2
+    assert np.abs(got[ok] - rs[ok]).max() < TOL
+    # without the flag nothing is dropped
+    _, _, c_all = ops.instance_disagreement(torch.from_numpy(emb).to(device), torch.from_numpy(keys).to(device), mode)
+    assert int(c_all.sum()) == n
+
+
+def test_disagreement_map_and_reward_match_numpy_semantics(device):
+    """N2: score gather + centre write + six inflate writes + reward, against numpy executing the reference's own
+    assignments (oracle/raster_oracle.py): last write wins, negative indices wrap, out-of-range assignment dropped."""
+    from oracle import raster_oracle as ro
+    rng = np.random.default_rng(23)
+    lower, upper = (-3.0, 0.0, -2.5), (4.2, 3.0, 3.7)
+    for case in range(4):
+        P, M = 20000, 25
+        pts = np.stack([rng.uniform(lower[0] + 0.2, upper[0] - 0.2, P), rng.uniform(0, 3, P),
+                        rng.uniform(lower[2] + 0.2, upper[2] - 0.2, P)], axis=1).astype(np.float32)
+        obj = rng.integers(0, M, size=P).astype(np.int64) + 5_000_000          # detection ids (matching.py:156-171)
+        if case == 1:        # points just left of / above the origin: negative indices that wrap
+            pts[:50, 0] = lower[0] - 0.03 - 0.04 * rng.uniform(0.0, 1.0, 50).astype(np.float32)
+            pts[50:90, 2] = lower[2] - 0.06
+        if case == 2:        # one point far outside: every assignment touching it is dropped whole
+            pts[0] = (upper[0] + 50.0, 1.0, 0.0)
+        if case == 3:        # a point on the last row/column: only SOME inflate assignments leave the grid
+            H, W, ox, oy = ro.grid_geometry(lower, upper)
+            pts[0] = ((W - 1 + ox + 0.5) * 0.025, 1.0, 0.0)
+        scores = rng.uniform(0.0, 0.6, M).astype(np.float32)
+        scores[::5] = 0.0                                                      # single-view objects: 0 -> not painted
+        ik = np.arange(M, dtype=np.int64) + 5_000_000
+        ref_map, ref_reward = ro.disagreement_map(pts, obj, {int(k): torch.tensor(v) for k, v in zip(ik, scores)},
+                                                  lower, upper)
+        got_map, got_reward = dis.disagreement_map(torch.from_numpy(pts).to(device), torch.from_numpy(obj).to(device),
+                                                   torch.from_numpy(ik).to(device), torch.from_numpy(scores).to(device),
+                                                   lower, upper)
+        assert got_map.shape == ref_map.shape
+        assert np.array_equal(got_map.cpu().numpy(), ref_map), f"case {case}: map differs"      # bit-exact
+        assert abs(float(got_reward) - ref_reward) <= 1e-5 * max(1.0, abs(ref_reward))
+        if case == 2:
+            assert ref_map.sum() == 0.0
+        if case == 0:
+            assert ref_map.sum() > 0
+    # empty point cloud
+    m0, r0 = dis.disagreement_map(torch.zeros((0, 3), device=device), torch.zeros((0,), dtype=torch.int64, device=device),
+                                  torch.zeros((0,), dtype=torch.int64, device=device), torch.zeros((0,), device=device),
+                                  lower, upper)
+    assert float(m0.abs().sum()) == 0.0 and float(r0) == 0.0

@@ -1,0 +1,171 @@
+"""GPU: episode-replay shape (BASELINE.json configs[2]) at reduced length -- frames + detector boxes -> crops ->
+captions -> cumulative per-instance disagreement with duplicate-view removal after every frame -> map + reward,
+against the CPU oracles on the same seeded inputs; and the long-caption shape (configs[4], seq_len 60)."""
+import numpy as np
+import pytest
+import torch
+
+from embodied_captioning_b200 import ops, synth
+from embodied_captioning_b200.captioner import transform as tr
+from embodied_captioning_b200.config import get_config
+from embodied_captioning_b200.engine import CaptionEngine
+from embodied_captioning_b200.episode import EpisodeReplay
+from oracle import disagreement_oracle as do
+from oracle import preprocess_oracle as po
+from oracle import raster_oracle as ro
+from oracle.coca_oracle import OracleCoCa
+
+pytestmark = pytest.mark.gpu
+
+
+def _caption_embedding(table):
+    """Stand-in for the reference's caption-text encoder (SBERT, absent offline): a deterministic bag-of-tokens
+    embedding, so that identical captions give bit-identical embeddings (what `unique(dim=0)` relies on)."""
+    def f(tokens, latent):
+        e = table.to(tokens.device)[tokens.clamp(min=0)]              # [N, T, D]
+        return e.sum(dim=1)
+    return f
+
+
+def test_episode_replay_matches_oracles(device):
+    cfg = get_config("coca_tiny")
+    sd = synth.make_state_dict(cfg, seed=1234)
+    eng = CaptionEngine("coca_tiny", None, device=device, decode_graph=True, state_dict=sd)
+    F_, K = 10, 8
+    frames, boxes, fidx, ids = synth.make_frames_and_boxes(F_, K, 480, 640, seed=31)
+    rng = np.random.default_rng(5)
+    ids = ids.copy()
+    fresh = rng.random(len(ids)) < 0.1                                 # ~10 % fresh detection ids (matching.py:156-171)
+    ids[fresh] = 5_000_000 + np.arange(int(fresh.sum()))
+    # repeat some detections exactly (same frame content + same box) so duplicate views really occur
+    frames[5] = frames[2]
+    boxes[5 * K:6 * K] = boxes[2 * K:3 * K]
+    ids[5 * K:6 * K] = ids[2 * K:3 * K]
+    perm = rng.permutation(len(ids))                                   # detections arrive in arbitrary order
+    table = torch.from_numpy(np.random.default_rng(9).normal(size=(cfg.vocab_size, 384)).astype(np.float32))
+    lower, upper = (-2.0, 0.0, -2.0), (2.0, 3.0, 2.0)
+    P = 4000
+    pts = np.stack([rng.uniform(-1.9, 1.9, P), rng.uniform(0, 3, P), rng.uniform(-1.9, 1.9, P)], 1).astype(np.float32)
+    pobj = rng.choice(np.unique(ids), size=P)
+    rep = EpisodeReplay(eng, embed_fn=_caption_embedding(table), dedup=True)
+    res = rep.run(torch.from_numpy(frames), boxes[perm], fidx[perm], ids[perm], policy=tr.POLICY_AGENT, seq_len=12,
+                  chunk_crops=32, points=pts, point_ids=pobj, bounds=(lower, upper))
+    ops.check_watchdog(device)
+    assert int(res.status.max()) == 0 and len(res.frames) == F_
+    order = perm[res.order]                                            # row r of the result = original detection order[r]
+    assert np.array_equal(fidx[order], np.sort(fidx))
+
+    # --- crops -> model input: bit-exact against the Pillow-exact oracle (numpy slice + transform)
+    ref_x, ref_rects = po.preprocess_boxes(frames, boxes[order], fidx[order], tr.POLICY_AGENT)
+    rects, _ = tr.box_rects(boxes[order], 480, 640, tr.POLICY_AGENT)
+    assert np.array_equal(rects, ref_rects)
+    _, f32, _ = tr.preprocess_boxes(torch.from_numpy(frames).to(device), boxes[order], fidx[order], tr.POLICY_AGENT,
+                                    want_f32=True)
+    assert np.array_equal(f32.cpu().numpy(), ref_x)
+
+    # --- captions: fp32 oracle on the same inputs
+    orc = OracleCoCa(cfg, sd)
+    lat_ref, embs_ref = orc.encode_image_tokens(torch.from_numpy(ref_x))
+    assert torch.nn.functional.cosine_similarity(res.latent.cpu(), lat_ref).min().item() >= 0.999
+    tok_ref = orc.generate(image_embs=embs_ref, seq_len=12, mode="kvcache", fixed_output_length=True)["text"]
+    same = (res.tokens.cpu()[:, :tok_ref.shape[1]] == tok_ref).all(dim=1)
+    print(f"episode replay: {len(order)} crops, identical greedy sequences on {same.float().mean() * 100:.1f}%")
+    # the duplicated detections must give bit-identical captions, hence bit-identical embeddings
+    inv = np.empty(len(order), dtype=np.int64)
+    inv[order] = np.arange(len(order))                                 # original detection index -> result row
+    dup_a, dup_b = inv[2 * K:3 * K], inv[5 * K:6 * K]
+    assert torch.equal(res.tokens[dup_a], res.tokens[dup_b])
+    assert torch.equal(res.embeddings[dup_a], res.embeddings[dup_b])
+
+    # --- cumulative per-frame disagreement with unique(dim=0), then map + reward, from the GPU's own embeddings
+    emb = res.embeddings.cpu().numpy()
+    k_sorted = ids[order]
+    saw_dedup = False
+    for fr in res.frames:
+        u = int(np.searchsorted(fidx[order], fr.frame, side="right"))
+        rk, rs, rc = do.instance_disagreement(emb[:u], k_sorted[:u], mode="full", dedup=True)
+        assert fr.inst_keys.cpu().tolist() == rk.tolist()              # grouping: bit-exact
+        assert fr.inst_counts.cpu().tolist() == rc.tolist()            # distinct-view counts: bit-exact
+        _, _, rc_all = do.instance_disagreement(emb[:u], k_sorted[:u], mode="full", dedup=False)
+        saw_dedup |= bool((rc_all != rc).any())
+        assert np.abs(fr.inst_scores.cpu().numpy() - rs).max() < 1e-3
+        seen = np.isin(pobj, rk)
+        # the oracle map is painted from the GPU's scores so that the map comparison is bit-exact on its own
+        cd = {int(k): torch.tensor(float(s), dtype=torch.float32) for k, s in zip(rk, fr.inst_scores.cpu().numpy())}
+        ref_map, ref_reward = ro.disagreement_map(pts[seen], pobj[seen], cd, lower, upper)
+        assert np.array_equal(fr.dmap.cpu().numpy(), ref_map)
+        assert abs(float(fr.reward) - ref_reward) <= 1e-5 * max(1.0, abs(ref_reward))
+    assert saw_dedup, "the test episode must exercise duplicate-view removal"
+
+
+def test_long_caption_shape_seq_len_60(device):
+    """BASELINE.json configs[4]: max 60 tokens (the reference never passes seq_len, SURVEY.md A7: an extrapolation
+    of the same loop).  KV caches, positional table and forced EOS at index 59 against the fp32 oracle."""
+    cfg = get_config("coca_small")
+    sd = synth.make_state_dict(cfg, seed=77)
+    eng = CaptionEngine("coca_small", None, device=device, decode_graph=True, state_dict=sd)
+    crops, ids = synth.make_instance_crops(4, 5, seed=8)               # 5 views per instance
+    x = torch.from_numpy(np.stack([po.transform(c) for c in crops]))
+    out = eng.caption_crops(torch.from_numpy(crops).to(device), torch.from_numpy(ids).to(device), seq_len=60)
+    ops.check_watchdog(device)
+    tok = out["tokens"].cpu()
+    assert tok.shape == (20, 60) and (tok[:, 0] == cfg.sot_token_id).all()
+    assert (tok[:, 1:5] != cfg.eos_token_id).all()
+    # a row ends on EOS *or* on a sampled PAD id (mask = last in {EOS, PAD}, coca_model.py:304); the others run
+    # to the end and get the forced EOS at the last slot (coca_model.py:317-318)
+    ended = ((tok[:, 1:59] == cfg.eos_token_id) | (tok[:, 1:59] == cfg.pad_token_id)).any(dim=1)
+    assert (~ended).any()
+    assert (tok[~ended, 59] == cfg.eos_token_id).all()
+    assert (tok[ended, 59] == cfg.pad_token_id).all()
+    orc = OracleCoCa(cfg, sd)
+    _, embs_ref = orc.encode_image_tokens(x)
+    ref = orc.generate(image_embs=embs_ref, seq_len=60, mode="kvcache", fixed_output_length=True)["text"]
+    # compare up to the first near-tie split per row: random-init logits are almost flat
+    agree = (tok == ref)
+    first_split = torch.where(agree.all(dim=1), torch.full((20,), 60), (~agree).float().argmax(dim=1))
+    print(f"seq_len 60: identical sequences {agree.all(dim=1).float().mean() * 100:.0f}%, "
+          f"median first split at token {int(first_split.median())}")
+    assert int(first_split.median()) >= 20
+    with pytest.raises(Exception):
+        eng.model.generate(None, image_embs=out["latent"][:, None, :].expand(-1, cfg.n_image_embs, -1).contiguous(),
+                           generation_type="top_k", seq_len=cfg.context_length + 5)
+
+
+def test_caption_frequency_table_matches_string_oracle(device):
+    """N4: per-instance caption histogram on token rows == counting strings (pseudocaptioner.py:156-177)."""
+    from embodied_captioning_b200.captioner import pseudocaptioner as pc
+    from oracle import pseudocaption_oracle as pco
+    rng = np.random.default_rng(41)
+    n, T, n_caps = 5000, 30, 60
+    vocab = rng.integers(1, 900, size=(n_caps, T))
+    vocab[:, 0] = 1022
+    for c in range(n_caps):                                           # EOS then PAD, like greedy decode output
+        L = int(rng.integers(6, T - 1))
+        vocab[c, L] = 1023; vocab[c, L + 1:] = 0
+    vocab[7] = vocab[3]; vocab[7, 4] += 1                              # near-duplicate captions
+    which = rng.integers(0, n_caps, size=n)
+    tokens = vocab[which]
+    eids = rng.integers(0, 3, size=n); oids = rng.integers(0, 40, size=n)
+    words = ["chair", "table", "lamp", "dog", "sofa", "room", "shelf", "plant"]
+    def decode(row):
+        return " ".join(words[int(t) % len(words)] for t in row[1:] if t not in (0, 1023))
+    got = pc.compute_captions_frequency(torch.from_numpy(tokens).to(device), eids, oids, decode)
+    ref = pco.captions_frequency([decode(r) for r in tokens], eids, oids, pc.BANNED_WORDS)
+    assert list(got.keys()) == list(ref.keys())                        # dict insertion order of the instances
+    assert got == ref
+    got_all = pc.compute_captions_frequency(torch.from_numpy(tokens).to(device), eids, oids, decode, apply_filter=False)
+    ref_all = pco.captions_frequency([decode(r) for r in tokens], eids, oids, (), apply_filter=False)
+    assert got_all == ref_all and sum(f for v in got_all.values() for f, _ in v) == n
+    # raw kernel output: ordered by (key, first occurrence), counts add up, first rows are first occurrences
+    keys = torch.from_numpy((eids.astype(np.int64) << 32) | oids.astype(np.int64)).to(device)
+    k, first, cnt = ops.caption_frequency(torch.from_numpy(tokens).to(device), keys)
+    k, first, cnt = k.cpu().numpy(), first.cpu().numpy(), cnt.cpu().numpy()
+    assert int(cnt.sum()) == n
+    assert all((k[i], first[i]) < (k[i + 1], first[i + 1]) for i in range(len(k) - 1))
+    seen = {}
+    for i in range(n):
+        seen.setdefault((int(keys[i]), tokens[i].tobytes()), i)
+    assert sorted(seen.values()) == sorted(first.tolist())
+    e0 = ops.caption_frequency(torch.zeros((0, T), dtype=torch.int32, device=device),
+                               torch.zeros((0,), dtype=torch.int64, device=device))
+    assert len(e0[0]) == 0
