@@ -97,6 +97,32 @@ def decoder_algorithmic_bytes(cfg, batch, steps):
     return total
 
 
+def gemm_algorithmic_bytes(cfg, batch):
+    """Algorithmic HBM bytes of the tcgen05 GEMM launches of one step that bench.py times (image tower + cross-K/V
+    projection): A (bf16) + W (bf16) + output (+ fp32 residual read) per launch, DESIGN.md section 3."""
+    G2 = (cfg.image_size // cfg.patch_size) ** 2
+    Mv, Mp = batch * (G2 + 1), batch * G2
+    W, E, T, Q = cfg.vision_width, cfg.embed_dim, cfg.text_width, cfg.n_queries
+    pk = -(-3 * cfg.patch_size ** 2 // 8) * 8
+
+    def g(M, N, K, out_bytes, resid=False):
+        return 2 * M * K + 2 * N * K + out_bytes * M * N + (4 * M * N if resid else 0)
+    per_layer = g(Mv, 3 * W, W, 2) + g(Mv, W, W, 4, True) + g(Mv, 4 * W, W, 2) + g(Mv, W, 4 * W, 4, True)
+    total = g(Mp, W, pk, 4) + cfg.vision_layers * per_layer + g(Mv, 2 * E, W, 2) + g(batch * Q, E, E, 4) + g(batch, E, E, 4)
+    total += cfg.mm_layers * g(batch * (Q - 1), 2 * T, T, 2)
+    launches = 1 + 4 * cfg.vision_layers + 3 + cfg.mm_layers
+    return total, launches
+
+
+def measured_gemm_traffic():
+    """Per-launch DRAM bytes of the same launches from the committed ncu launch list (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.isfile(p) and MODEL == "coca_ViT-L-14" and BATCH == 1024:
+        d = json.load(open(p))
+        return d["dram_bytes_per_launch"], d["source"]
+    return None, None
+
+
 def run_reference(args, rank, world):
     """`--impl reference`: the reference's own CPU algorithm for this path (oracle port: Pillow-exact preprocess,
     fp32 CoCa, generate() with batch 1 and no KV cache, python-loop disagreement) on all host threads."""
@@ -288,6 +314,8 @@ def main():
 
     gemm_tflops = (g_fl.value / (g_ms.value * 1e-3) / 1e12) if g_ms.value > 0 else 0.0
     peak_tf = peaks["bf16_tflops_sustained"]
+    alg_bytes, alg_launches = gemm_algorithmic_bytes(cfg, BATCH)
+    traffic, traffic_src = measured_gemm_traffic()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -298,8 +326,14 @@ def main():
                    "l2_hygiene": "per-step working set (>= 9 GB activations + K/V) is far larger than the 126 MB L2",
                    "parallelism": f"batch-sharded x{world}" + (", NCCL all-gather of latents+keys" if world > 1 else "")},
         "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": gemm_tflops / peak_tf if peak_tf else None, "traffic": None,
-                     "kernel": "gemm_tcgen05_kernel (image tower + cross-K/V projection GEMMs)",
+                     "frac": gemm_tflops / peak_tf if peak_tf else None, "traffic": traffic,
+                     "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                     "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": alg_bytes / alg_launches,
+                     "algorithmic_flops_per_launch": (g_fl.value / g_n.value) if g_n.value else None,
+                     "avg_launch_ms": (g_ms.value / g_n.value) if g_n.value else None,
+                     "kernel": "gemm_tcgen05_pair_kernel<256,*> (tcgen05 cta_group::2; image tower + cross-K/V "
+                               "projection GEMM launches of the step)",
                      "launches_timed": int(g_n.value), "peak_source": peaks["source"] + " bf16_tflops_sustained",
                      "encoder_only": {"ms": t_enc, "tflops": BATCH * ENC_GFLOP.get(MODEL, 0) / t_enc if t_enc else None,
                                       "frac_of_burst_peak": (BATCH * ENC_GFLOP.get(MODEL, 0) / t_enc / peaks["bf16_tflops"])

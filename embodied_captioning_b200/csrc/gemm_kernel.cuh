@@ -101,7 +101,10 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  // relaxed: the only data this arrival publishes is "my tcgen05.ld of the accumulator stage has completed", which
+  // tcgen05.wait::ld + tcgen05.fence::before_thread_sync order already.  The release.cluster form costs an ERRBAR
+  // that waits for every earlier global store of the tile to drain (7 % of the stall samples of the fc1 GEMM).
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA load whose completion bytes are credited to an mbarrier of the pair's leader CTA (shared::cluster address)
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* tmap, int c0, int c1, uint32_t leader_bar) {
@@ -219,73 +222,84 @@ struct EpiParams {
   const int* skip_flag;
 };
 
-// Epilogue of one 128 x BN accumulator tile for one epilogue warp: its 32-row TMEM lane quadrant (`quad`), the
-// column half `half`, 32 columns at a time: tcgen05.ld -> bias / GELU / arg-max in registers -> swizzled
-// shared-memory transpose -> coalesced 128-byte global row segments.  `row0` = first global row of the slab.
-// residual rows of one 32 x 32 chunk for this lane: 8 row groups x (4 columns at `gcol`)
-__device__ __forceinline__ void load_resid_chunk(const EpiParams& p, int row0, int gcol, int lane, float4 (&rsd)[8]) {
+// One 32 x 32 chunk.  kFull = the whole chunk lies inside [M, N]: no per-element bound predicates (the interior
+// of the matrix, i.e. nearly every chunk; they were a third of the epilogue's instructions).
+template <int BN, int EPI, bool kFull>
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& p, uint32_t taddr, int row0, int gcol0, int lane,
+                                               uint32_t stg, int cur_len, float& best_v, int& best_i) {
+  const int cc = lane & 7;
+  const int gcol = gcol0 + cc * 4;
+  // The residual may alias the output (in-place residual stream): every element is read and written by the same
+  // thread.  All eight loads of the chunk are issued before the TMEM load and the transpose so that their latency
+  // is hidden (prefetching a whole chunk further ahead measured no better: 822 vs 842 TFLOP/s on out_proj).
+  float4 rsd[8];
+  if (EPI == EPI_F32_RESID) {
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int grow = row0 + it * 4 + (lane >> 3);
-    rsd[it] = (grow < p.M && gcol < p.N)
-                  ? *reinterpret_cast<const float4*>(p.residual + (size_t)grow * p.ldr + gcol)
-                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = 0; it < 8; ++it) {
+      const int grow = row0 + it * 4 + (lane >> 3);
+      rsd[it] = (kFull || (grow < p.M && gcol < p.N))
+                    ? *reinterpret_cast<const float4*>(p.residual + (size_t)grow * p.ldr + gcol)
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
-}
-
-template <int BN, int EPI>
-__device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_acc, int row0, int n_blk, int quad,
-                                              int half, int lane, uint32_t stg, int cur_len) {
-  constexpr int kColsPerWarp = BN / 2;
-  constexpr int kChunks = kColsPerWarp / 32;
-  float best_v = -INFINITY; int best_i = 0;
-#pragma unroll 1
-  for (int c = 0; c < kChunks; ++c) {
-    const int col_in_tile = half * kColsPerWarp + c * 32;
-    const int gcol0 = n_blk * BN + col_in_tile;
-    const int cc = lane & 7;
-    const int gcol = gcol0 + cc * 4;
-    // The residual may alias the output (in-place residual stream): every element is read and written by the same
-    // thread.  All eight loads of the chunk are issued before the TMEM load and the transpose so that their latency
-    // is hidden (prefetching a whole chunk further ahead measured no better: 822 vs 842 TFLOP/s on out_proj).
-    float4 rsd[8];
-    if (EPI == EPI_F32_RESID) load_resid_chunk(p, row0, gcol, lane, rsd);
-    uint32_t r[32];
-    ptx::tmem_ld_32x32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)col_in_tile, r);
-    ptx::tmem_ld_wait();
-    if (gcol0 >= p.N) continue;           // warp-uniform
-    float v[32];
+  uint32_t r[32];
+  ptx::tmem_ld_32x32(taddr, r);
+  ptx::tmem_ld_wait();
+  float v[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (p.bias != nullptr) {
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.bias != nullptr) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (gcol0 + j < p.N) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol0 + j));
-          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    for (int j = 0; j < 32; j += 4) {
+      if (kFull || gcol0 + j < p.N) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+  }
+  if (EPI == EPI_BF16_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  }
+  if (EPI == EPI_ARGMAX) {
+    if (kFull || row0 + lane < p.M) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = gcol0 + j;
+        if (kFull || col < p.N) {
+          float x = v[j];
+          if (col == p.eos_col && cur_len < p.min_len) x = -INFINITY;
+          v[j] = x;
+          if (x > best_v) { best_v = x; best_i = col; }
         }
       }
     }
-    if (EPI == EPI_BF16_GELU) {
+    if (p.logits == nullptr) return;      // warp-uniform: nothing to store
+  }
+  if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
+    // ---- bf16 output: pack in registers, transpose 32 rows x 64 B through shared memory (16-byte unit u of row r
+    //      lives at unit u ^ ((r >> 1) & 3): conflict-free both ways), then 4 lanes x 16 B = one 64-byte row segment
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t a0 = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]), a1 = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+      const uint32_t a2 = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), a3 = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+      ptx::st_shared_v4(stg + (uint32_t)lane * 64u + (uint32_t)((g ^ ((lane >> 1) & 3)) * 16), __uint_as_float(a0),
+                        __uint_as_float(a1), __uint_as_float(a2), __uint_as_float(a3));
     }
-    if (EPI == EPI_ARGMAX) {
-      if (row0 + lane < p.M) {
+    __syncwarp();
+    const int cu = lane & 3;
+    const int gc = gcol0 + cu * 8;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = gcol0 + j;
-          if (col < p.N) {
-            float x = v[j];
-            if (col == p.eos_col && cur_len < p.min_len) x = -INFINITY;
-            v[j] = x;
-            if (x > best_v) { best_v = x; best_i = col; }
-          }
-        }
-      }
-      if (p.logits == nullptr) continue;  // warp-uniform: nothing to store
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + (lane >> 2);
+      const int grow = row0 + rr;
+      const float4 o = ptx::ld_shared_v4(stg + (uint32_t)rr * 64u + (uint32_t)((cu ^ ((rr >> 1) & 3)) * 16));
+      if (kFull || (grow < p.M && gc < p.N))
+        *reinterpret_cast<float4*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo + gc) = o;
     }
-    // ---- transpose through shared memory: lane = row  ->  8 lanes x 16 B = one 128-byte row segment
+    __syncwarp();                           // staging buffer is reused by the next chunk
+  } else {
+    // ---- fp32 output: transpose through shared memory: lane = row  ->  8 lanes x 16 B = one 128-byte row segment
     //      (16-byte unit u of row r lives at unit u ^ (r & 7): conflict-free in both directions)
 #pragma unroll
     for (int g = 0; g < 8; ++g)
@@ -297,13 +311,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
       const int rr = it * 4 + (lane >> 3);
       const int grow = row0 + rr;
       float4 o = ptx::ld_shared_v4(stg + (uint32_t)rr * 128u + (uint32_t)((cc ^ (rr & 7)) * 16));
-      if (grow < p.M && gcol < p.N) {
-        if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
-          uint2 q;
-          q.x = pack_bf16x2(o.x, o.y);
-          q.y = pack_bf16x2(o.z, o.w);
-          *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo + gcol) = q;
-        } else if (EPI == EPI_F32 || EPI == EPI_F32_RESID) {
+      if (kFull || (grow < p.M && gcol < p.N)) {
+        if (EPI == EPI_F32 || EPI == EPI_F32_RESID) {
           if (EPI == EPI_F32_RESID) {
             o.x += rsd[it].x; o.y += rsd[it].y; o.z += rsd[it].z; o.w += rsd[it].w;
           }
@@ -315,7 +324,29 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
       }
     }
     __syncwarp();                           // staging buffer is reused by the next chunk
+  }
+}
 
+// Epilogue of one 128 x BN accumulator tile for one epilogue warp: its 32-row TMEM lane quadrant (`quad`), the
+// column half `half`, 32 columns at a time: tcgen05.ld -> bias / GELU / arg-max in registers -> swizzled
+// shared-memory transpose -> coalesced global row segments.  `row0` = first global row of the slab.
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_acc, int row0, int n_blk, int quad,
+                                              int half, int lane, uint32_t stg, int cur_len) {
+  constexpr int kColsPerWarp = BN / 2;
+  constexpr int kChunks = kColsPerWarp / 32;
+  float best_v = -INFINITY; int best_i = 0;
+  const bool rows_full = row0 + 32 <= p.M;
+#pragma unroll 1
+  for (int c = 0; c < kChunks; ++c) {
+    const int col_in_tile = half * kColsPerWarp + c * 32;
+    const int gcol0 = n_blk * BN + col_in_tile;
+    const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)col_in_tile;
+    if (gcol0 >= p.N) continue;           // warp-uniform: nothing of this chunk is inside the matrix
+    if (rows_full && gcol0 + 32 <= p.N)
+      epilogue_chunk<BN, EPI, true>(p, taddr, row0, gcol0, lane, stg, cur_len, best_v, best_i);
+    else
+      epilogue_chunk<BN, EPI, false>(p, taddr, row0, gcol0, lane, stg, cur_len, best_v, best_i);
   }
   if (EPI == EPI_ARGMAX && row0 + lane < p.M) {
     const size_t slot = (size_t)(row0 + lane) * p.n_parts + (size_t)(n_blk * 2 + half);

@@ -166,11 +166,11 @@ def test_decoder_row_chains_are_bit_identical(device, graph):
     for chains in (1, 2, 3, 4):
         model.set_decode_chains(chains)
         o = model.generate(None, image_embs=embs, generation_type="top_k", seq_len=9, fixed_output_length=True)
-        outs.append((o["text"].clone(), torch.stack([l for l in o["logits"]]).clone()))
+        outs.append((o["text"].clone(), [l.clone() for l in o["logits"]]))      # ragged list: rows finish early
     ops.check_watchdog(device)
     for tok, lg in outs[1:]:
         assert torch.equal(tok, outs[0][0])
-        assert torch.equal(lg, outs[0][1])
+        assert len(lg) == len(outs[0][1]) and all(torch.equal(a, b) for a, b in zip(lg, outs[0][1]))
     text = outs[0][0][:, :6]
     model.set_decode_chains(1)
     a = model.forward(None, text, image_latent=torch.zeros(n, cfg.embed_dim), image_embs=embs, output_labels=False)["logits"]
