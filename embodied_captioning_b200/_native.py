@@ -26,6 +26,8 @@ EXPORTS = [
     "ec_launch_count", "ec_profile_gemm", "ec_profile_gemm_read", "ec_attention_fused_qkv",
     "ec_disagreement_map_workspace_bytes", "ec_disagreement_map",
     "ec_caption_frequency_workspace_bytes", "ec_caption_frequency",
+    "ec_textenc_create", "ec_textenc_destroy", "ec_textenc_set_tensor", "ec_textenc_finalize",
+    "ec_textenc_workspace_bytes", "ec_textenc_encode",
 ]
 
 
@@ -38,6 +40,11 @@ class EcConfig(C.Structure):
         "embed_dim", "image_size", "patch_size", "vision_width", "vision_layers", "vision_head_dim",
         "pooler_heads", "n_queries", "text_width", "text_heads", "text_layers", "mm_layers", "mm_heads",
         "context_length", "vocab_size", "sot_token_id", "eos_token_id", "pad_token_id")]
+
+
+class EcTextEncConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("vocab_size", "hidden", "layers", "heads", "intermediate", "max_positions",
+                                         "type_vocab")] + [("layer_norm_eps", C.c_float)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -89,6 +96,13 @@ def lib() -> C.CDLL:
     L.ec_caption_frequency_workspace_bytes.argtypes = [i32]
     L.ec_caption_frequency_workspace_bytes.restype = sz
     L.ec_caption_frequency.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp, vp, vp, sz, vp]
+    L.ec_textenc_create.argtypes = [C.POINTER(EcTextEncConfig), C.c_int, C.POINTER(vp)]
+    L.ec_textenc_destroy.argtypes = [vp]
+    L.ec_textenc_set_tensor.argtypes = [vp, C.c_char_p, vp, i64]
+    L.ec_textenc_finalize.argtypes = [vp]
+    L.ec_textenc_workspace_bytes.argtypes = [vp, i32, i32]
+    L.ec_textenc_workspace_bytes.restype = sz
+    L.ec_textenc_encode.argtypes = [vp, vp, vp, i32, i32, vp, vp, sz, vp]
     L.ec_launch_count.argtypes = []
     L.ec_launch_count.restype = C.c_int64
     L.ec_profile_gemm.argtypes = [i32]

@@ -39,6 +39,9 @@ __global__ void __launch_bounds__(kAttnThreads) attention_full_kernel(AttnArgs a
   const int b = blockIdx.x, h = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tg = lane & 3;
+  // per-sequence key count (padded text batches); keys beyond it are masked like the padding of the last chunk
+  const int skv = (a.kv_len != nullptr) ? max(1, min(a.kv_len[b], a.skv)) : a.skv;
+  const int kv_end = ((skv + kKvChunk - 1) / kKvChunk) * kKvChunk;
 
   // ---- stage K, V of this (crop, head); rows >= skv are zero so that masked columns contribute exactly 0
   {
@@ -48,7 +51,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_full_kernel(AttnArgs a
     for (int idx = tid; idx < skv_pad * CPR; idx += kAttnThreads) {
       const int r = idx / CPR, c = idx % CPR;
       uint4 kv4 = make_uint4(0, 0, 0, 0), vv4 = make_uint4(0, 0, 0, 0);
-      if (r < a.skv) {
+      if (r < skv) {
         kv4 = *reinterpret_cast<const uint4*>(kg + (size_t)r * a.k_rs + c * 8);
         vv4 = *reinterpret_cast<const uint4*>(vg + (size_t)r * a.v_rs + c * 8);
       }
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_full_kernel(AttnArgs a
 #pragma unroll
     for (int i = 0; i < DT; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
 
-    for (int kv0 = 0; kv0 < skv_pad; kv0 += kKvChunk) {
+    for (int kv0 = 0; kv0 < kv_end; kv0 += kKvChunk) {
       float s[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
@@ -102,8 +105,8 @@ __global__ void __launch_bounds__(kAttnThreads) attention_full_kernel(AttnArgs a
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int c = kv0 + nt * 8 + tg * 2;
-        if (c >= a.skv) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-        if (c + 1 >= a.skv) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+        if (c >= skv) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+        if (c + 1 >= skv) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
         mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
         mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
       }

@@ -33,6 +33,7 @@ struct AttnArgs {
   bf16* o; long long o_bs, o_rs;
   int batch, heads, sq, skv, head_dim;  // head_dim in {32, 64, 96}
   float scale;                          // 1/sqrt(head_dim)
+  const int* kv_len = nullptr;          // optional per-batch key count (<= skv): padded text batches
 };
 int attention_full(const AttnArgs& a, cudaStream_t stream);
 

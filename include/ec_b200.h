@@ -104,6 +104,26 @@ int ec_instance_disagreement_peers(const float* const* peers_dev, int32_t world,
                                    float* out_score_dev, int32_t* out_count_dev, int32_t* out_m_dev, void* ws_dev,
                                    size_t ws_bytes, void* stream);
 
+/* ---- caption-text encoder (MiniLM-class BERT sentence encoder): replaces `self.encoder.encode(caption)` of
+ * `SentenceTransformer("all-MiniLM-L6-v2")` (agents/goal_exploration/goal_exploration.py:57,102-103;
+ * detector/pseudolabeler.py:568,651,677) for WordPiece ids that are already on the device.  Weights are loaded by
+ * HF `BertModel` state-dict names ("embeddings.word_embeddings.weight", "encoder.layer.0.attention.self.query.weight",
+ * ...; "bert." / "0.auto_model." prefixes accepted).  ids int32 [n, seq] (row = [CLS] ... [SEP] pad...), lens int32 [n]
+ * = number of real tokens per row (the attention mask is a prefix mask); out f32 [n, hidden] = L2-normalised masked
+ * mean of the last hidden state. */
+typedef struct ec_textenc_config {
+  int32_t vocab_size, hidden, layers, heads, intermediate, max_positions, type_vocab;
+  float layer_norm_eps;
+} ec_textenc_config;
+typedef struct ec_textenc ec_textenc;
+int ec_textenc_create(const ec_textenc_config* cfg, int device, ec_textenc** out);
+int ec_textenc_destroy(ec_textenc* t);
+int ec_textenc_set_tensor(ec_textenc* t, const char* name, const float* host_data, int64_t numel);
+int ec_textenc_finalize(ec_textenc* t);
+size_t ec_textenc_workspace_bytes(const ec_textenc* t, int32_t n, int32_t seq);
+int ec_textenc_encode(ec_textenc* t, const int32_t* ids_dev, const int32_t* lens_dev, int32_t n, int32_t seq,
+                      float* out_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
 /* ---- caption frequency table per instance: replaces `PseudoCaptioner.compute_captions_frequency`
  * (captioner/pseudocaptioner.py:156-177; grouping key :137) on token-id rows.  tokens int32 [n, ld] (first t columns
  * compared), keys int64 [n].  One entry per distinct (key, caption): out_key, out_first (row of its first occurrence),

@@ -5,7 +5,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 files=("$@")
-[ ${#files[@]} -eq 0 ] && files=(tests/test_gpu_kernels.py tests/test_gpu_preprocess.py tests/test_gpu_disagreement.py tests/test_gpu_model.py)
+[ ${#files[@]} -eq 0 ] && files=(tests/test_gpu_kernels.py tests/test_gpu_preprocess.py tests/test_gpu_disagreement.py tests/test_gpu_model.py tests/test_gpu_episode.py tests/test_gpu_textenc.py)
 nvidia-smi --query-gpu=name,memory.total,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gpu_info.txt 2>&1
 rc_all=0
 for f in "${files[@]}"; do
