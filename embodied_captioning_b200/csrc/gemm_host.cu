@@ -88,9 +88,10 @@ static int launch_tile(const GemmArgs& a, cudaStream_t stream) {
   return EC_OK;
 }
 
-template <int BN, int EPI>
-static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
+template <int BN, int EPI, int EW>
+static int launch_pair_ew(const GemmArgs& a, cudaStream_t stream) {
   using Cfg = PairCfg<BN>;
+  constexpr int kSmem = Cfg::template smem_bytes<EPI, EW>();
   CUtensorMap ta, tw;
   EC_TRY(make_tmap(&ta, a.A, a.M, a.K, a.lda, kBM));
   EC_TRY(make_tmap(&tw, a.W, a.N, a.K, a.ldw, BN / 2));
@@ -103,14 +104,25 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
   const int clusters = std::min(tiles_m * tiles_n, num_sms() / 2);
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
-    EC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::kSmemBytes));
+    EC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<BN, EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kSmem));
     attr_set = true;
   }
   note_launches(1);
-  EC_CHECK_CUDA(launch_kernel(gemm_tcgen05_pair_kernel<BN, EPI>, dim3(2 * clusters), dim3(kThreads),
-                              (size_t)Cfg::kSmemBytes, stream, ta, tw, p, a.K, tiles_m, tiles_n));
+  EC_CHECK_CUDA(launch_kernel(gemm_tcgen05_pair_kernel<BN, EPI, EW>, dim3(2 * clusters), dim3((kFirstEpiWarp + EW) * 32),
+                              (size_t)kSmem, stream, ta, tw, p, a.K, tiles_m, tiles_n));
   return EC_OK;
+}
+
+template <int BN, int EPI>
+static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
+  using Cfg = PairCfg<BN>;
+  // 16 epilogue warps for the bf16-output epilogues (bias / GELU), 8 for fp32 residual and arg-max
+  static const int ew_env = [] { const char* e = getenv("EC_GEMM_EW"); return e ? atoi(e) : 0; }();
+  constexpr bool kCan16 = (EPI == EPI_BF16 || EPI == EPI_BF16_GELU);
+  constexpr int EW = kCan16 ? 16 : 8;
+  if (kCan16 && ew_env == 8) return launch_pair_ew<BN, EPI, 8>(a, stream);
+  return launch_pair_ew<BN, EPI, EW>(a, stream);
 }
 
 // CTA-pair (cta_group::2) kernel for GEMMs with enough 256 x 256 tiles to occupy every SM pair

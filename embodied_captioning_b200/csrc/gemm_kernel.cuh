@@ -140,6 +140,13 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
                : "memory");
 }
 
+// one lane of a converged warp (the instruction must be reached by all 32 lanes)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
@@ -330,10 +337,11 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, uint32_t tadd
 // Epilogue of one 128 x BN accumulator tile for one epilogue warp: its 32-row TMEM lane quadrant (`quad`), the
 // column half `half`, 32 columns at a time: tcgen05.ld -> bias / GELU / arg-max in registers -> swizzled
 // shared-memory transpose -> coalesced global row segments.  `row0` = first global row of the slab.
-template <int BN, int EPI>
+template <int BN, int EPI, int PARTS = 2>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_acc, int row0, int n_blk, int quad,
                                               int half, int lane, uint32_t stg, int cur_len) {
-  constexpr int kColsPerWarp = BN / 2;
+  static_assert(EPI != EPI_ARGMAX || PARTS == 2, "arg-max partial slots are laid out for two column halves");
+  constexpr int kColsPerWarp = BN / PARTS;
   constexpr int kChunks = kColsPerWarp / 32;
   float best_v = -INFINITY; int best_i = 0;
   const bool rows_full = row0 + 32 <= p.M;
@@ -427,9 +435,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer (one thread)
-    if (lane == 0) {
+    // ===================================================================== MMA issuer
+    // The whole warp walks the loop (warp-uniform control flow and addresses, so the descriptors live in uniform
+    // registers) and ONE elected lane issues the tcgen05 instructions.  With a single-lane branch around the loop
+    // ptxas spent ~25 instructions per UMMA on election + register broadcasts, ~110 per k-block, and the tensor
+    // pipe waited on this one warp: 85 % active for the plain epilogue, 67 % next to the GELU epilogue warps.
+    {
       constexpr uint32_t idesc = make_idesc<BN>();
+      const uint64_t adesc0 = make_smem_desc(smem_a0), bdesc0 = make_smem_desc(smem_b0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -439,18 +452,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int kb = 0; kb < num_kb; ++kb) {
           if (!bounded_wait(full_bar(stage), phase, 3)) goto done;
           ptx::tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_a0 + stage * Cfg::kABytes);
-          const uint64_t bdesc = make_smem_desc(smem_b0 + stage * Cfg::kBBytes);
+          const uint64_t adesc = adesc0 + (uint64_t)((stage * Cfg::kABytes) >> 4);
+          const uint64_t bdesc = bdesc0 + (uint64_t)((stage * Cfg::kBBytes) >> 4);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            ptx::umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                           (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+              ptx::umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                             (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            ptx::umma_commit(empty_bar(stage));          // frees the smem stage when the MMAs retire
           }
-          ptx::umma_commit(empty_bar(stage));          // frees the smem stage when the MMAs retire
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
-        ptx::umma_commit(tfull_bar(acc));              // accumulator ready for the epilogue
+        if (ptx::elect_one()) ptx::umma_commit(tfull_bar(acc));   // accumulator ready for the epilogue
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -494,6 +511,11 @@ done:
 // shared-memory operand reads of the tensor pipe).  The leader CTA (cluster rank 0) issues every MMA; both CTAs' TMA
 // loads credit the leader's `full` barrier; the leader's tcgen05.commit multicasts the `empty` / `accumulator full`
 // arrivals to both CTAs; both CTAs' epilogue warps release the accumulator stage on the leader's barrier.
+// bytes of transpose staging per epilogue warp: 32 rows x 64 B for the packed-bf16 epilogues, 32 x 128 B otherwise
+template <int EPI> __host__ __device__ constexpr int kPairEpiStageBytes() {
+  return (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) ? 32 * 64 : kEpiStageBytes;
+}
+
 template <int BN> struct PairCfg {
   static constexpr int kABytes = kBM * kBK * 2;                // this CTA's 128 rows
   static constexpr int kBBytes = (BN / 2) * kBK * 2;           // this CTA's half of the W tile
@@ -501,8 +523,11 @@ template <int BN> struct PairCfg {
   static constexpr int kStages = (BN == 256) ? 6 : 8;
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kBarBytes = 1024;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + kBarBytes + 1024 /*align*/;
-  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
+  template <int EPI, int EW> static constexpr int smem_bytes() {
+    return kStages * kStageBytes + EW * kPairEpiStageBytes<EPI>() + kBarBytes + 1024 /*align*/;
+  }
+  static_assert(kStages * kStageBytes + kEpiWarps * kEpiStageBytes + kBarBytes + 1024 <= 227 * 1024,
+                "shared memory budget exceeded");
 };
 
 template <int BN>
@@ -510,8 +535,10 @@ __device__ __forceinline__ constexpr uint32_t make_idesc_pair() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * kBM) >> 4) << 24);
 }
 
-template <int BN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+// EW = epilogue warps per CTA: 8 (two column halves per TMEM lane quadrant) or 16 (four column quarters; bf16
+// epilogues only -- the GELU epilogue is latency-bound with two warps per scheduler: tensor pipe 63 % active)
+template <int BN, int EPI, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((kFirstEpiWarp + EW) * 32, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                          EpiParams p, int K, int tiles_m, int tiles_n) {
   using Cfg = PairCfg<BN>;
@@ -522,7 +549,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const uint32_t smem_a0 = smem_base;
   const uint32_t smem_b0 = smem_base + Cfg::kStages * Cfg::kABytes;
   const uint32_t smem_epi = smem_base + Cfg::kStages * Cfg::kStageBytes;
-  const uint32_t bar0 = smem_epi + kEpiWarps * kEpiStageBytes;
+  const uint32_t bar0 = smem_epi + EW * kPairEpiStageBytes<EPI>();
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * Cfg::kStages + s); };
@@ -550,7 +577,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);                   // one multicast commit
-      ptx::mbar_init(tempty_bar(s), 2 * kEpiWarps);      // leader's: the epilogue warps of both CTAs
+      ptx::mbar_init(tempty_bar(s), 2 * EW);      // leader's: the epilogue warps of both CTAs
     }
     ptx::fence_barrier_init();
   }
@@ -588,9 +615,11 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer (leader CTA, one thread)
-    if (lane == 0 && rank == 0) {
+    // ===================================================================== MMA issuer (leader CTA; warp-uniform
+    // loop, one elected lane issues -- see the 1-CTA kernel)
+    if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_pair<BN>();
+      const uint64_t adesc0 = make_smem_desc(smem_a0), bdesc0 = make_smem_desc(smem_b0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
@@ -600,16 +629,20 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int kb = 0; kb < num_kb; ++kb) {
           if (!bounded_wait(full_bar(stage), phase, 3)) goto done;
           ptx::tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_a0 + stage * Cfg::kABytes);
-          const uint64_t bdesc = make_smem_desc(smem_b0 + stage * Cfg::kBBytes);
+          const uint64_t adesc = adesc0 + (uint64_t)((stage * Cfg::kABytes) >> 4);
+          const uint64_t bdesc = bdesc0 + (uint64_t)((stage * Cfg::kBBytes) >> 4);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k)
-            ptx::umma_bf16_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                (kb > 0 || k > 0) ? 1u : 0u);
-          ptx::umma_commit_pair(empty_bar(stage), (uint16_t)3);     // frees the stage in both CTAs
+            for (int k = 0; k < kBK / kUmmaK; ++k)
+              ptx::umma_bf16_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                  (kb > 0 || k > 0) ? 1u : 0u);
+            ptx::umma_commit_pair(empty_bar(stage), (uint16_t)3);     // frees the stage in both CTAs
+          }
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
-        ptx::umma_commit_pair(tfull_bar(acc), (uint16_t)3);         // accumulator ready in both CTAs
+        if (ptx::elect_one()) ptx::umma_commit_pair(tfull_bar(acc), (uint16_t)3);   // accumulator ready in both CTAs
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -618,7 +651,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int e = warp - kFirstEpiWarp;
     const int quad = warp & 3;
     const int half = e >> 2;
-    const uint32_t stg = smem_epi + (uint32_t)e * kEpiStageBytes;
+    const uint32_t stg = smem_epi + (uint32_t)e * kPairEpiStageBytes<EPI>();
     int acc = 0; uint32_t acc_phase = 0;
     int cur_len = 0;
     if (EPI == EPI_ARGMAX) cur_len = (p.cur_len != nullptr) ? *p.cur_len : (1 << 30);
@@ -626,8 +659,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
       if (!bounded_wait(tfull_bar(acc), acc_phase, 4)) break;
       ptx::tc_fence_after();
-      epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m_blk * (2 * kBM) + (int)rank * kBM + quad * 32, n_blk,
-                             quad, half, lane, stg, cur_len);
+      epilogue_tile<BN, EPI, EW / 4>(p, tmem_base + (uint32_t)(acc * BN), m_blk * (2 * kBM) + (int)rank * kBM + quad * 32,
+                                     n_blk, quad, half, lane, stg, cur_len);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(tempty_bar(acc), 0));
