@@ -97,6 +97,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// one lane of a converged warp (reached by all 32 lanes)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -200,8 +206,9 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ============================================================ TMA producer
-    if (lane == 0) {
+    // ============================================================ TMA producer (warp-uniform loop, one elected
+    // lane issues: a single-lane branch costs ~25 election/broadcast instructions per bulk-tensor instruction)
+    {
       uint32_t kv_it = 0, q_it = 0;
       for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         const int b = pair / a.heads, h = pair % a.heads;
@@ -209,27 +216,34 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
         const int kvb = kv_it & 1;
         if (!await(BAR(KV_EMPTY, kvb), ((kv_it >> 1) & 1) ^ 1u, 1)) goto done;
         const int kv_boxes = (n_mma + kATile - 1) / kATile;
-        aptx::mbar_expect_tx(BAR(KV_FULL, kvb), (uint32_t)(2 * (kv_boxes * kAQBytes + (tail_box ? kAKeysTail * 128 : 0))));
-        for (int i = 0; i < kv_boxes; ++i) {
-          aptx::tma_load_2d(k_smem(kvb) + i * kAQBytes, &tm128, a.k_col0 + h * kAD, row0 + i * kATile, BAR(KV_FULL, kvb));
-          aptx::tma_load_2d(v_smem(kvb) + i * kAQBytes, &tm128, a.v_col0 + h * kAD, row0 + i * kATile, BAR(KV_FULL, kvb));
+        if (aptx::elect_one()) {
+          aptx::mbar_expect_tx(BAR(KV_FULL, kvb), (uint32_t)(2 * (kv_boxes * kAQBytes + (tail_box ? kAKeysTail * 128 : 0))));
+          for (int i = 0; i < kv_boxes; ++i) {
+            aptx::tma_load_2d(k_smem(kvb) + i * kAQBytes, &tm128, a.k_col0 + h * kAD, row0 + i * kATile, BAR(KV_FULL, kvb));
+            aptx::tma_load_2d(v_smem(kvb) + i * kAQBytes, &tm128, a.v_col0 + h * kAD, row0 + i * kATile, BAR(KV_FULL, kvb));
+          }
+          if (tail_box) {
+            aptx::tma_load_2d(k_smem(kvb) + 2 * kAQBytes, &tm16, a.k_col0 + h * kAD, row0 + kAKeysMma, BAR(KV_FULL, kvb));
+            aptx::tma_load_2d(v_smem(kvb) + 2 * kAQBytes, &tm16, a.v_col0 + h * kAD, row0 + kAKeysMma, BAR(KV_FULL, kvb));
+          }
         }
-        if (tail_box) {
-          aptx::tma_load_2d(k_smem(kvb) + 2 * kAQBytes, &tm16, a.k_col0 + h * kAD, row0 + kAKeysMma, BAR(KV_FULL, kvb));
-          aptx::tma_load_2d(v_smem(kvb) + 2 * kAQBytes, &tm16, a.v_col0 + h * kAD, row0 + kAKeysMma, BAR(KV_FULL, kvb));
-        }
+        __syncwarp();
         ++kv_it;
         for (int t = 0; t < n_qtiles; ++t, ++q_it) {
           const int qb = q_it & 1;
           if (!await(BAR(Q_EMPTY, qb), ((q_it >> 1) & 1) ^ 1u, 2)) goto done;
-          aptx::mbar_expect_tx(BAR(Q_FULL, qb), kAQBytes);
-          aptx::tma_load_2d(q_smem(qb), &tm128, a.q_col0 + h * kAD, row0 + t * kATile, BAR(Q_FULL, qb));
+          if (aptx::elect_one()) {
+            aptx::mbar_expect_tx(BAR(Q_FULL, qb), kAQBytes);
+            aptx::tma_load_2d(q_smem(qb), &tm128, a.q_col0 + h * kAD, row0 + t * kATile, BAR(Q_FULL, qb));
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer
-    if (lane == 0) {
+    // ============================================================ MMA issuer (warp-uniform loop, one elected lane
+    // issues the 4 + 16 tcgen05.mma of a tile back to back)
+    {
       const uint32_t id_qk = idesc_qk(n_mma), id_pv = idesc_pv();
       uint32_t kv_it = 0, it = 0;            // `it` counts q tiles globally: buffers alternate with it & 1
       int prev_valid = 0; uint32_t prev_it = 0; int prev_kvb = 0; bool prev_last = false;
@@ -239,10 +253,14 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
         aptx::tc_fence_after();
         const uint32_t t_p = tmem_base + (uint32_t)(sb * 256);
         const uint32_t t_o = t_p + 128;
-        for (int k = 0; k < n_mma / 16; ++k)
-          aptx::umma_ts(t_o, t_p + (uint32_t)(k * 8), desc_mnmajor(v_smem(pkvb) + (uint32_t)k * 2048u), id_pv, k > 0 ? 1u : 0u);
-        aptx::umma_commit(BAR(O_FULL, sb));
-        if (last_of_pair) aptx::umma_commit(BAR(KV_EMPTY, pkvb));
+        const uint64_t vdesc0 = desc_mnmajor(v_smem(pkvb));
+        if (aptx::elect_one()) {
+          for (int k = 0; k < n_mma / 16; ++k)
+            aptx::umma_ts(t_o, t_p + (uint32_t)(k * 8), vdesc0 + (uint64_t)(k * (2048 >> 4)), id_pv, k > 0 ? 1u : 0u);
+          aptx::umma_commit(BAR(O_FULL, sb));
+          if (last_of_pair) aptx::umma_commit(BAR(KV_EMPTY, pkvb));
+        }
+        __syncwarp();
         return true;
       };
       for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
@@ -254,12 +272,15 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
           if (!await(BAR(Q_FULL, sb), (it >> 1) & 1, 6)) goto done;
           aptx::tc_fence_after();
           const uint32_t t_s = tmem_base + (uint32_t)(sb * 256);
+          const uint64_t qdesc = desc_kmajor(q_smem(sb)), kdesc = desc_kmajor(k_smem(kvb));
+          if (aptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kAD / 16; ++k)
-            aptx::umma_ss(t_s, desc_kmajor(q_smem(sb)) + (uint64_t)(k * 2), desc_kmajor(k_smem(kvb)) + (uint64_t)(k * 2),
-                          id_qk, k > 0 ? 1u : 0u);
-          aptx::umma_commit(BAR(S_FULL, sb));
-          aptx::umma_commit(BAR(Q_EMPTY, sb));
+            for (int k = 0; k < kAD / 16; ++k)
+              aptx::umma_ss(t_s, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), id_qk, k > 0 ? 1u : 0u);
+            aptx::umma_commit(BAR(S_FULL, sb));
+            aptx::umma_commit(BAR(Q_EMPTY, sb));
+          }
+          __syncwarp();
           if (prev_valid) { if (!issue_pv(prev_it, prev_kvb, prev_last)) goto done; }
           prev_valid = 1; prev_it = it; prev_kvb = kvb; prev_last = (t == n_qtiles - 1);
         }

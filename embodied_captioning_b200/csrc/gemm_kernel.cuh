@@ -420,16 +420,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (skip) {
     // fall through to the teardown
   } else if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================================== TMA producer (warp-uniform loop, one
+    // elected lane issues)
+    {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           if (!bounded_wait(empty_bar(stage), phase ^ 1u, 1)) goto done;
-          ptx::mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          ptx::tma_load_2d(smem_a0 + stage * Cfg::kABytes, &tmap_a, kb * kBK, m_blk * kBM, full_bar(stage));
-          ptx::tma_load_2d(smem_b0 + stage * Cfg::kBBytes, &tmap_w, kb * kBK, n_blk * BN, full_bar(stage));
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            ptx::tma_load_2d(smem_a0 + stage * Cfg::kABytes, &tmap_a, kb * kBK, m_blk * kBM, full_bar(stage));
+            ptx::tma_load_2d(smem_b0 + stage * Cfg::kBBytes, &tmap_w, kb * kBK, n_blk * BN, full_bar(stage));
+          }
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -597,8 +601,9 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (skip) {
     // fall through to the teardown
   } else if (warp == 0) {
-    // ===================================================================== TMA producer (both CTAs)
-    if (lane == 0) {
+    // ===================================================================== TMA producer (both CTAs; warp-uniform
+    // loop, one elected lane issues)
+    {
       int stage = 0; uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
         const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
@@ -607,9 +612,12 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int kb = 0; kb < num_kb; ++kb) {
           if (!bounded_wait(empty_bar(stage), phase ^ 1u, 1)) goto done;
           const uint32_t lead_full = ptx::mapa_shared(full_bar(stage), 0);
-          if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-          ptx::tma_load_2d_pair(smem_a0 + stage * Cfg::kABytes, &tmap_a, kb * kBK, a_row, lead_full);
-          ptx::tma_load_2d_pair(smem_b0 + stage * Cfg::kBBytes, &tmap_w, kb * kBK, b_row, lead_full);
+          if (ptx::elect_one()) {
+            if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+            ptx::tma_load_2d_pair(smem_a0 + stage * Cfg::kABytes, &tmap_a, kb * kBK, a_row, lead_full);
+            ptx::tma_load_2d_pair(smem_b0 + stage * Cfg::kBBytes, &tmap_w, kb * kBK, b_row, lead_full);
+          }
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
       }
