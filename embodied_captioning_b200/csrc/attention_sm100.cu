@@ -108,6 +108,30 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Blackwell packed-pair fp32 pipe (FFMA2 / FADD2) and three-input max (FMNMX3): half the instructions per element
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -162,6 +186,10 @@ struct AttnSm100Args {
   float scale_log2;                     // (1/sqrt(64)) * log2(e)
 };
 
+// kMask = false: every key column the tensor core produces is a real key (n_valid_mma == n_mma, e.g. 257 tokens),
+// so the two softmax passes carry no per-element bound checks (a third of their instructions; the softmax warps are
+// what bounds this kernel: two warps per scheduler, issue slots 43 % busy, tensor pipe 14 %).
+template <bool kMask>
 __global__ void __launch_bounds__(kAThreads, 1)
 attention_sm100_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16,
                        AttnSm100Args a) {
@@ -352,15 +380,25 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
             aptx::tmem_ld_wait();
             const bool has_b = c0 + 32 < n_mma;
             if (has_b) aptx::tmem_ld32(t_s + (uint32_t)(c0 + 32), vb);
+            if (!kMask) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < n_valid_mma) mx = fmaxf(mx, __uint_as_float(va[j]));
+              for (int j = 0; j < 32; j += 2) mx = aptx::max3(mx, __uint_as_float(va[j]), __uint_as_float(va[j + 1]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j < n_valid_mma) mx = fmaxf(mx, __uint_as_float(va[j]));
+            }
             if (has_b) {
               aptx::tmem_ld_wait();
               if (c0 + 64 < n_mma) aptx::tmem_ld32(t_s + (uint32_t)(c0 + 64), va);
+              if (!kMask) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c0 + 32 + j < n_valid_mma) mx = fmaxf(mx, __uint_as_float(vb[j]));
+                for (int j = 0; j < 32; j += 2) mx = aptx::max3(mx, __uint_as_float(vb[j]), __uint_as_float(vb[j + 1]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (c0 + 32 + j < n_valid_mma) mx = fmaxf(mx, __uint_as_float(vb[j]));
+              }
             }
           }
         }
@@ -371,13 +409,18 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
         float sum = 0.f;
         {
           uint32_t va[32], vb[32];
+          const uint64_t sc2 = aptx::pack_f32x2(a.scale_log2, a.scale_log2), nms2 = aptx::pack_f32x2(-ms, -ms);
+          uint64_t sum2 = aptx::pack_f32x2(0.f, 0.f);
           auto emit = [&](const uint32_t (&v)[32], int c0) {
             uint32_t pk[16];
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              const float p0 = (c0 + j < n_valid_mma) ? aptx::ex2(fmaf(__uint_as_float(v[j]), a.scale_log2, -ms)) : 0.f;
-              const float p1 = (c0 + j + 1 < n_valid_mma) ? aptx::ex2(fmaf(__uint_as_float(v[j + 1]), a.scale_log2, -ms)) : 0.f;
-              sum += p0 + p1;
+              float e0, e1;
+              aptx::unpack_f32x2(aptx::fma_f32x2(aptx::pack_f32x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc2, nms2),
+                                 e0, e1);
+              const float p0 = (!kMask || c0 + j < n_valid_mma) ? aptx::ex2(e0) : 0.f;
+              const float p1 = (!kMask || c0 + j + 1 < n_valid_mma) ? aptx::ex2(e1) : 0.f;
+              sum2 = aptx::add_f32x2(sum2, aptx::pack_f32x2(p0, p1));
               pk[j >> 1] = pack_bf16x2(p0, p1);
             }
             aptx::tmem_st16(t_s + (uint32_t)(c0 >> 1), pk);   // P overwrites S columns that were already consumed
@@ -394,6 +437,9 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
               emit(vb, c0 + 32);
             }
           }
+          float s_lo, s_hi;
+          aptx::unpack_f32x2(sum2, s_lo, s_hi);
+          sum = s_lo + s_hi;
         }
         // tail keys: their P.V contribution is formed now, so every direct read of the pair's K/V tiles by this
         // thread happens before its P_READY arrive (the last PV commit of the pair then safely frees the tiles)
@@ -497,7 +543,8 @@ int attention_sm100_fused_qkv(const bf16* qkv, long long ld, int q_col0, int k_c
   EC_TRY(encode_map(&tm16, qkv, rows, cols, ld, kAKeysTail));
   static bool attr = false;
   if (!attr) {
-    EC_CHECK_CUDA(cudaFuncSetAttribute(attention_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kASmemBytes));
+    EC_CHECK_CUDA(cudaFuncSetAttribute(attention_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kASmemBytes));
+    EC_CHECK_CUDA(cudaFuncSetAttribute(attention_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kASmemBytes));
     attr = true;
   }
   AttnSm100Args a;
@@ -505,7 +552,11 @@ int attention_sm100_fused_qkv(const bf16* qkv, long long ld, int q_col0, int k_c
   a.q_col0 = q_col0; a.k_col0 = k_col0; a.v_col0 = v_col0;
   a.scale_log2 = 0.125f * 1.4426950408889634f;
   const int grid = std::min(batch * heads, num_sms());
-  attention_sm100_kernel<<<grid, kAThreads, kASmemBytes, stream>>>(tm128, tm16, a);
+  const int n_mma = std::min((seq + 15) & ~15, kAKeysMma);
+  if (std::min(seq, kAKeysMma) == n_mma)
+    attention_sm100_kernel<false><<<grid, kAThreads, kASmemBytes, stream>>>(tm128, tm16, a);
+  else
+    attention_sm100_kernel<true><<<grid, kAThreads, kASmemBytes, stream>>>(tm128, tm16, a);
   EC_POST_LAUNCH();
   return EC_OK;
 }
