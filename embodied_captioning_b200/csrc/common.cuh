@@ -126,6 +126,46 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return (x >= 0.f) ? fmaf(-x, w, x) : x * w;
 }
 
+// ---- packed-pair fp32 (Blackwell FFMA2 / FMUL2): two elements per instruction
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// gelu_erf for two elements at once: same polynomial, the Horner chain runs on the packed-pair pipe
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const float z0 = fminf(fabsf(x0) * 0.70710678118654752440f, 4.2f);
+  const float z1 = fminf(fabsf(x1) * 0.70710678118654752440f, 4.2f);
+  const uint64_t z = pack_f32x2(z0, z1);
+  uint64_t q = fma_f32x2(pack_f32x2(-2.074870827e-05f, -2.074870827e-05f), z, pack_f32x2(4.926680704e-04f, 4.926680704e-04f));
+  q = fma_f32x2(q, z, pack_f32x2(-5.263294093e-03f, -5.263294093e-03f));
+  q = fma_f32x2(q, z, pack_f32x2(3.403032571e-02f, 3.403032571e-02f));
+  q = fma_f32x2(q, z, pack_f32x2(-1.526207328e-01f, -1.526207328e-01f));
+  q = fma_f32x2(q, z, pack_f32x2(-9.169294834e-01f, -9.169294834e-01f));
+  q = fma_f32x2(q, z, pack_f32x2(-1.628114700e+00f, -1.628114700e+00f));
+  q = fma_f32x2(q, z, pack_f32x2(-9.999952912e-01f, -9.999952912e-01f));
+  float q0, q1, w0, w1;
+  unpack_f32x2(q, q0, q1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w0) : "f"(q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w1) : "f"(q1));
+  x0 = (x0 >= 0.f) ? fmaf(-x0, w0, x0) : x0 * w0;
+  x1 = (x1 >= 0.f) ? fmaf(-x1, w1, x1) : x1 * w1;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -266,7 +266,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, uint32_t tadd
   }
   if (EPI == EPI_BF16_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < 32; j += 2) gelu_erf2(v[j], v[j + 1]);
   }
   if (EPI == EPI_ARGMAX) {
     if (kFull || row0 + lane < p.M) {
