@@ -22,7 +22,7 @@ EXPORTS = [
     "ec_model_finalize", "ec_model_set_option", "ec_preprocess_crops", "ec_encode_workspace_bytes",
     "ec_encode_image", "ec_decode_workspace_bytes", "ec_decode_greedy", "ec_forward_logits",
     "ec_disagreement_workspace_bytes", "ec_instance_disagreement", "ec_instance_disagreement_peers",
-    "ec_gemm_bf16", "ec_gemm_argmax", "ec_layernorm", "ec_attention", "ec_check_watchdog",
+    "ec_gemm_bf16", "ec_gemm_bf16_ln", "ec_gemm_argmax", "ec_layernorm", "ec_attention", "ec_check_watchdog",
     "ec_launch_count", "ec_profile_gemm", "ec_profile_gemm_read", "ec_attention_fused_qkv",
     "ec_disagreement_map_workspace_bytes", "ec_disagreement_map",
     "ec_caption_frequency_workspace_bytes", "ec_caption_frequency",
@@ -85,6 +85,7 @@ def lib() -> C.CDLL:
     L.ec_instance_disagreement_peers.argtypes = [vp, i32, i32, i64, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp,
                                                  sz, vp]
     L.ec_gemm_bf16.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp, i32, i32, i32, vp]
+    L.ec_gemm_bf16_ln.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp, i32, vp, vp, vp, i32, vp, vp]
     L.ec_gemm_argmax.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, sz, vp]
     L.ec_layernorm.argtypes = [vp, i64, vp, vp, vp, i64, i32, i32, i32, vp]
     L.ec_attention.argtypes = [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64, i32, i32, i32, i32, i32, vp]

@@ -169,6 +169,19 @@ int ec_gemm_bf16(const void* a, int32_t lda, const void* w, int32_t ldw, int32_t
   return gemm_bf16(g, (GemmEpilogue)epilogue, as_stream(stream));
 }
 
+int ec_gemm_bf16_ln(const void* a, int32_t lda, const void* w, int32_t ldw, int32_t m, int32_t n, int32_t k,
+                    const float* bias, const float* residual, int32_t ldr, float* out, int32_t ldo, const float* ln_gamma,
+                    const float* ln_beta, void* ln_out_bf16, int32_t ld_ln, int32_t* ln_counters, void* stream) {
+  EC_REQUIRE(a && w && residual && out && ln_gamma && ln_beta && ln_out_bf16 && ln_counters, EC_ERR_INVALID,
+             "ec_gemm_bf16_ln: null argument");
+  GemmArgs g{};
+  g.A = reinterpret_cast<const bf16*>(a); g.lda = lda; g.W = reinterpret_cast<const bf16*>(w); g.ldw = ldw;
+  g.M = m; g.N = n; g.K = k; g.bias = bias; g.residual = residual; g.ldr = ldr; g.out = out; g.ldo = ldo;
+  g.ln_gamma = ln_gamma; g.ln_beta = ln_beta; g.ln_out = reinterpret_cast<bf16*>(ln_out_bf16); g.ld_ln = ld_ln;
+  g.ln_counters = ln_counters;
+  return gemm_bf16(g, EPI_F32_RESID, as_stream(stream));
+}
+
 // arg-max of each logits row through the fused vocab-head epilogue (+ the select kernel's reduction)
 __global__ void argmax_parts_kernel(const float* __restrict__ pv, const int* __restrict__ pi, int n_parts, int rows,
                                     int* __restrict__ out) {

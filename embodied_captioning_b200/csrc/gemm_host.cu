@@ -74,6 +74,8 @@ static int launch_tile(const GemmArgs& a, cudaStream_t stream) {
   p.logits = a.logits; p.ld_logits = a.ld_logits; p.logits_step_stride = a.logits_step_stride; p.part_val = a.part_val; p.part_idx = a.part_idx;
   p.n_parts = a.n_parts; p.eos_col = a.eos_col; p.cur_len = a.cur_len; p.min_len = a.min_len;
   p.skip_flag = a.skip_flag;
+  p.ln_g = a.ln_gamma; p.ln_b = a.ln_beta; p.ln_out = a.ln_out; p.ld_ln = a.ld_ln; p.ln_cnt = a.ln_counters;
+  p.ln_tiles_n = ceil_div(a.N, BN);
   const int tiles_m = ceil_div(a.M, kBM), tiles_n = ceil_div(a.N, BN);
   const int grid = std::min(tiles_m * tiles_n, num_sms());
   static bool attr_set = false;   // per template instantiation
@@ -100,6 +102,8 @@ static int launch_pair_ew(const GemmArgs& a, cudaStream_t stream) {
   p.logits = a.logits; p.ld_logits = a.ld_logits; p.logits_step_stride = a.logits_step_stride; p.part_val = a.part_val; p.part_idx = a.part_idx;
   p.n_parts = a.n_parts; p.eos_col = a.eos_col; p.cur_len = a.cur_len; p.min_len = a.min_len;
   p.skip_flag = a.skip_flag;
+  p.ln_g = a.ln_gamma; p.ln_b = a.ln_beta; p.ln_out = a.ln_out; p.ld_ln = a.ld_ln; p.ln_cnt = a.ln_counters;
+  p.ln_tiles_n = ceil_div(a.N, BN);
   const int tiles_m = ceil_div(a.M, 2 * kBM), tiles_n = ceil_div(a.N, BN);
   const int clusters = std::min(tiles_m * tiles_n, num_sms() / 2);
   static bool attr_set = false;   // per template instantiation
@@ -211,6 +215,12 @@ static int gemm_dispatch(const GemmArgs& a, GemmEpilogue epi, cudaStream_t strea
   }
   if (epi == EPI_F32_RESID)
     EC_REQUIRE(a.residual != nullptr && a.ldr % 4 == 0, EC_ERR_INVALID, "residual epilogue needs a residual pointer");
+  if (a.ln_out != nullptr) {
+    EC_REQUIRE(epi == EPI_F32_RESID, EC_ERR_INVALID, "the fused LayerNorm tail belongs to the residual epilogue");
+    EC_REQUIRE(a.ln_gamma && a.ln_beta && a.ln_counters, EC_ERR_INVALID, "fused LayerNorm tail: null parameter");
+    EC_REQUIRE(a.N % 4 == 0 && a.N <= kLnTailMaxVec * 128 && a.ld_ln % 4 == 0, EC_ERR_UNSUPPORTED,
+               "fused LayerNorm tail: row width %d unsupported", a.N);
+  }
   if (a.bias) EC_REQUIRE((reinterpret_cast<uintptr_t>(a.bias) & 15u) == 0, EC_ERR_INVALID, "bias not 16-byte aligned");
   switch (epi) {
     case EPI_BF16: return launch_epi<EPI_BF16>(a, stream);
@@ -260,6 +270,7 @@ int gemm_reference_simt(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream
   p.M = a.M; p.N = a.N; p.bias = a.bias; p.residual = a.residual; p.ldr = a.ldr; p.out = a.out; p.ldo = a.ldo;
   p.logits = a.logits; p.ld_logits = a.ld_logits; p.logits_step_stride = a.logits_step_stride; p.part_val = a.part_val; p.part_idx = a.part_idx;
   p.n_parts = a.n_parts; p.eos_col = a.eos_col; p.cur_len = a.cur_len; p.min_len = a.min_len; p.skip_flag = nullptr;
+  p.ln_g = nullptr; p.ln_b = nullptr; p.ln_out = nullptr; p.ld_ln = 0; p.ln_cnt = nullptr; p.ln_tiles_n = 0;
   dim3 grid(ceil_div(a.N, 128), a.M);
   gemm_simt_kernel<<<grid, 128, 0, stream>>>(a.A, a.lda, a.W, a.ldw, a.M, a.N, a.K, p, (int)epi);
   EC_POST_LAUNCH();

@@ -227,6 +227,8 @@ struct EpiParams {
   float* part_val; int* part_idx; int n_parts;
   int eos_col; const int* cur_len; int min_len;
   const int* skip_flag;
+  // fused LayerNorm tail (EPI_F32_RESID only, ln_out != nullptr): see ln_tail()
+  const float* ln_g; const float* ln_b; bf16* ln_out; int ld_ln; int* ln_cnt; int ln_tiles_n;
 };
 
 // One 32 x 32 chunk.  kFull = the whole chunk lies inside [M, N]: no per-element bound predicates (the interior
@@ -363,6 +365,73 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused LayerNorm tail of the residual GEMMs.  The LayerNorm that follows out_proj / c_proj needs whole rows, which
+// are spread over `tiles_n` CTAs.  Every CTA counts its finished tile on a per-128-row counter (stores -> fence ->
+// atomicAdd); the CTA whose increment completes the row block re-reads those 128 rows (L2-hot: they were written
+// microseconds ago), normalises them and writes the bf16 operand of the next GEMM.  That removes the separate
+// LayerNorm launch (one of every seven kernels of a decoder step) and its cold HBM read of the residual stream
+// in the image tower.  Called by all `n_warps` epilogue warps of the CTA with `bar_id` a free named barrier.
+constexpr int kLnTailMaxVec = 8;     // row width <= 1024
+
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void ln_tail(const EpiParams& p, int row_base, int e, int n_warps, int lane, int bar_id,
+                                        volatile int* s_flag) {
+  // all epilogue warps of this CTA have stored their part of the tile
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(n_warps * 32) : "memory");
+  if (e == 0 && lane == 0) {
+    __threadfence();
+    const int old = atomicAdd(p.ln_cnt + row_base / kBM, 1);
+    const int last = (old == p.ln_tiles_n - 1) ? 1 : 0;
+    if (last) p.ln_cnt[row_base / kBM] = 0;          // re-armed for the next launch
+    *s_flag = last;
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(n_warps * 32) : "memory");
+  if (*s_flag == 0) return;
+  __threadfence();
+  const int width = p.N, nvec = width >> 2;
+  for (int r = e; r < kBM; r += n_warps) {
+    const int row = row_base + r;
+    if (row >= p.M) break;
+    const float* xr = reinterpret_cast<const float*>(p.out) + (size_t)row * p.ldo;
+    float4 v[kLnTailMaxVec];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnTailMaxVec; ++i) {
+      const int c = lane + i * 32;
+      v[i] = (c < nvec) ? ld_cg_f4(xr + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / (float)width;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnTailMaxVec; ++i) {
+      if (lane + i * 32 < nvec) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)width + 1e-5f);      // same arithmetic as layernorm.cu
+    bf16* yr = p.ln_out + (size_t)row * p.ld_ln;
+#pragma unroll
+    for (int i = 0; i < kLnTailMaxVec; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_g) + c), b = __ldg(reinterpret_cast<const float4*>(p.ln_b) + c);
+        uint2 pk;
+        pk.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+        pk.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+        reinterpret_cast<uint2*>(yr)[c] = pk;
+      }
+    }
+  }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
@@ -495,6 +564,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (EPI == EPI_F32_RESID && p.ln_out != nullptr)
+        ln_tail(p, m_blk * kBM, e, kEpiWarps, lane, 1, reinterpret_cast<volatile int*>(tmem_slot_ptr + 1));
     }
     pdl_trigger_bottom();    // per-CTA trigger: the first epilogue warp that has stored its last tile
   }
@@ -673,6 +744,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(tempty_bar(acc), 0));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (EPI == EPI_F32_RESID && p.ln_out != nullptr)
+        ln_tail(p, m_blk * (2 * kBM) + (int)rank * kBM, e, EW, lane, 1, reinterpret_cast<volatile int*>(tmem_slot_ptr + 1));
     }
     pdl_trigger_bottom();
   }

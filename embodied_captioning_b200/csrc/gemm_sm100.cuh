@@ -33,6 +33,10 @@ struct GemmArgs {
   int eos_col;                    // column forced to -inf when *cur_len < min_len
   const int* cur_len; int min_len;
   const int* skip_flag;           // device int; kernel returns immediately when *skip_flag != 0 (nullable)
+  // EPI_F32_RESID only: fused LayerNorm tail.  When ln_out != nullptr the kernel also writes
+  // ln_out[M, N] (bf16) = LayerNorm(out rows; ln_gamma, ln_beta, eps 1e-5) once a 128-row block of `out` is complete.
+  // ln_counters: >= ceil(M / 128) ints, zero before the first launch (the kernel re-arms them); N <= 1024, N % 4 == 0.
+  const float* ln_gamma; const float* ln_beta; bf16* ln_out; int ld_ln; int* ln_counters;
 };
 
 // number of arg-max partial slots per row produced by EPI_ARGMAX for vocabulary size N

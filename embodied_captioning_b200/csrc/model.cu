@@ -58,6 +58,20 @@ Model::Model(const ec_config& c, int dev) : cfg(c), device(dev) {
   dcross.resize(c.mm_layers);
   patch_k = 3 * c.patch_size * c.patch_size;
   patch_ld = (int)align_up((size_t)patch_k, 8);
+  const size_t n_cnt = kLnCountersEncoder + (size_t)kMaxChains * kLnCountersPerChain;
+  if (cudaSetDevice(dev) == cudaSuccess && cudaMalloc(&ln_counters, n_cnt * sizeof(int)) == cudaSuccess) {
+    cudaMemset(ln_counters, 0, n_cnt * sizeof(int));
+    owned.push_back(ln_counters);
+  } else {
+    ln_counters = nullptr;
+    fuse_ln = false;
+  }
+  // Measured on B200 (profiles/r01_fused_ln.txt): the fused tail is bit-exact but SLOWER -- one CTA normalises each
+  // 128-row block (latency-bound row loop on the GEMM's critical path) where the stand-alone kernel spreads the rows
+  // over every SM at the HBM roofline, and every tile pays two named barriers + a device-scope fence + an atomic.
+  // Encoder 180 -> 220 ms, decoder 113 -> 150 ms at 1024 crops.  Opt-in only (EC_FUSE_LN=1).
+  static const int env_fuse = [] { const char* e = getenv("EC_FUSE_LN"); return e ? atoi(e) : 0; }();
+  if (env_fuse == 0) fuse_ln = false;
 }
 
 Model::~Model() {
@@ -225,11 +239,19 @@ int Model::finalize(cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------------
 // transformer block helpers
 // ---------------------------------------------------------------------------------------------------
+struct FusedLn {      // LayerNorm applied to the rows of a residual GEMM's output by the GEMM itself (gemm_kernel.cuh::ln_tail)
+  const float* g = nullptr; const float* b = nullptr; bf16* out = nullptr; int ld = 0; int* counters = nullptr;
+};
+
 static int linear(const bf16* A, int lda, const bf16* W, int ldw, const float* bias, int M, int N, int K, void* out,
-                  int ldo, GemmEpilogue epi, const float* resid, int ldr, const int* skip, cudaStream_t s) {
+                  int ldo, GemmEpilogue epi, const float* resid, int ldr, const int* skip, cudaStream_t s,
+                  const FusedLn* ln = nullptr) {
   GemmArgs g{};
   g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.M = M; g.N = N; g.K = K; g.bias = bias;
   g.residual = resid; g.ldr = ldr; g.out = out; g.ldo = ldo; g.skip_flag = skip;
+  if (ln != nullptr && ln->out != nullptr) {
+    g.ln_gamma = ln->g; g.ln_beta = ln->b; g.ln_out = ln->out; g.ld_ln = ln->ld; g.ln_counters = ln->counters;
+  }
   return gemm_bf16(g, epi, s);
 }
 
@@ -305,9 +327,11 @@ int Model::encode_image(const bf16* x, int n, float* latent, float* embs, void* 
   EC_TRY(linear(w.patches, patch_ld, w_conv1, patch_ld, nullptr, n * G2, W, patch_k, w.patch_emb, W, EPI_F32, nullptr, 0,
                 nullptr, s));
   EC_TRY(vision_embed_ln_pre(w.patch_emb, cls_emb, vis_pos, ln_pre_g, ln_pre_b, w.resid, n, TV, W, s));
+  // Every LayerNorm except the first is computed by the residual GEMM that completes its input rows (fused tail).
+  const bool fuse = fuse_ln && ceil_div(Mv, 128) <= kLnCountersEncoder;
   for (int l = 0; l < cfg.vision_layers; ++l) {
     const Block& b = vblocks[l];
-    EC_TRY(layernorm(w.resid, W, b.ln1_g, b.ln1_b, w.ln, W, true, Mv, W, nullptr, s));
+    if (l == 0 || !fuse) EC_TRY(layernorm(w.resid, W, b.ln1_g, b.ln1_b, w.ln, W, true, Mv, W, nullptr, s));
     EC_TRY(linear(w.ln, W, b.w_qkv, W, b.b_qkv, Mv, 3 * W, W, w.qkv, 3 * W, EPI_BF16, nullptr, 0, nullptr, s));
     AttnArgs a{};
     a.q = w.qkv; a.k = w.qkv + W; a.v = w.qkv + 2 * W;
@@ -319,13 +343,18 @@ int Model::encode_image(const bf16* x, int n, float* latent, float* embs, void* 
       EC_TRY(attention_sm100_fused_qkv(w.qkv, 3 * W, 0, W, 2 * W, w.att, (long long)TV * W, W, n, heads, TV, s));
     else
       EC_TRY(attention_full(a, s));
-    EC_TRY(linear(w.att, W, b.w_out, W, b.b_out, Mv, W, W, w.resid, W, EPI_F32_RESID, w.resid, W, nullptr, s));
-    EC_TRY(layernorm(w.resid, W, b.ln2_g, b.ln2_b, w.ln, W, true, Mv, W, nullptr, s));
+    FusedLn ln2{b.ln2_g, b.ln2_b, fuse ? w.ln : nullptr, W, ln_counters};
+    EC_TRY(linear(w.att, W, b.w_out, W, b.b_out, Mv, W, W, w.resid, W, EPI_F32_RESID, w.resid, W, nullptr, s, &ln2));
+    if (!fuse) EC_TRY(layernorm(w.resid, W, b.ln2_g, b.ln2_b, w.ln, W, true, Mv, W, nullptr, s));
     EC_TRY(linear(w.ln, W, b.w_fc1, W, b.b_fc1, Mv, 4 * W, W, w.fc1, 4 * W, EPI_BF16_GELU, nullptr, 0, nullptr, s));
-    EC_TRY(linear(w.fc1, 4 * W, b.w_fc2, 4 * W, b.b_fc2, Mv, W, 4 * W, w.resid, W, EPI_F32_RESID, w.resid, W, nullptr, s));
+    const bool last = (l + 1 == cfg.vision_layers);     // the pooler's ln_k follows the last block
+    FusedLn nxt{last ? ln_k_g : vblocks[l + 1].ln1_g, last ? ln_k_b : vblocks[l + 1].ln1_b, fuse ? w.ln : nullptr, W,
+                ln_counters};
+    EC_TRY(linear(w.fc1, 4 * W, b.w_fc2, 4 * W, b.b_fc2, Mv, W, 4 * W, w.resid, W, EPI_F32_RESID, w.resid, W, nullptr, s,
+                  &nxt));
   }
   // attentional pooler: k = v = ln_k(x), q precomputed
-  EC_TRY(layernorm(w.resid, W, ln_k_g, ln_k_b, w.ln, W, true, Mv, W, nullptr, s));
+  if (!fuse) EC_TRY(layernorm(w.resid, W, ln_k_g, ln_k_b, w.ln, W, true, Mv, W, nullptr, s));
   EC_TRY(linear(w.ln, W, w_pool_kv, W, b_pool_qkv + E, Mv, 2 * E, W, w.pool_kv, 2 * E, EPI_BF16, nullptr, 0, nullptr, s));
   {
     const int hd = E / cfg.pooler_heads;
@@ -358,6 +387,7 @@ struct DecodeWs {
   bf16* ln_kv; bf16* cross_kv; bf16* tk; bf16* tv; bf16* dk; bf16* dv;
   float* x; bf16* ln; bf16* qkv; bf16* att; bf16* fc1; bf16* q;
   float* part_val; int* part_idx; unsigned char* finished; DecodeState* st; int* tokens_tf;
+  int* ln_cnt;           // fused-LayerNorm row-block counters of this chain
   size_t cache_layer;    // elements between the self-K/V caches of consecutive layers (whole batch)
   size_t cross_layer;    // elements between the cross-K/V caches of consecutive layers (whole batch)
   size_t bytes;
@@ -374,6 +404,7 @@ static DecodeWs slice_rows(const Model& m, const DecodeWs& w, int r0, int seq_le
   v.x += r * T; v.ln += r * T; v.qkv += r * 3 * T; v.att += r * T; v.fc1 += r * 4 * T; v.q += r * T;
   v.part_val += r * parts; v.part_idx += r * parts; v.finished += r; v.tokens_tf += r * L;
   v.st += chain;
+  v.ln_cnt = m.ln_counters + kLnCountersEncoder + chain * kLnCountersPerChain;
   return v;
 }
 
@@ -401,6 +432,7 @@ static DecodeWs carve_decode(const Model& m, void* ws, int n, int seq_len) {
   w.finished = b.take<unsigned char>((size_t)n);
   w.st = b.take<DecodeState>(kMaxChains);
   w.tokens_tf = b.take<int>((size_t)n * L);
+  w.ln_cnt = m.ln_counters + kLnCountersEncoder;
   w.cache_layer = (size_t)n * L * T;
   w.cross_layer = (size_t)n * NK * 2 * T;
   w.bytes = b.off;
@@ -411,30 +443,39 @@ size_t Model::decode_workspace_bytes(int n, int seq_len) const {
   return carve_decode(*this, nullptr, std::max(n, 1), std::max(seq_len, 2)).bytes;
 }
 
+// `ln1_done`: w.ln already holds ln_1(x) (written by the previous block's fused tail); `next_g/next_b`: the LayerNorm
+// that follows this block (next block's ln_1 or ln_final), fused into c_proj when `fuse_ln` is on.
 int Model::self_block(const Block& b, const DecodeWs& w, bf16* kc, bf16* vc, int n, int max_len, int heads,
-                      cudaStream_t s) {
+                      bool ln1_done, const float* next_g, const float* next_b, cudaStream_t s) {
   const int T = cfg.text_width;
   const int* skip = &w.st->done;
-  EC_TRY(layernorm(w.x, T, b.ln1_g, b.ln1_b, w.ln, T, true, n, T, skip, s));
+  const bool fuse = decoder_fuse(n);
+  if (!ln1_done) EC_TRY(layernorm(w.x, T, b.ln1_g, b.ln1_b, w.ln, T, true, n, T, skip, s));
   EC_TRY(linear(w.ln, T, b.w_qkv, T, b.b_qkv, n, 3 * T, T, w.qkv, 3 * T, EPI_BF16, nullptr, 0, skip, s));
   EC_TRY(decode_self_attention(w.qkv, kc, vc, w.att, n, heads, T / heads, max_len, w.finished, w.st, s));
-  EC_TRY(linear(w.att, T, b.w_out, T, b.b_out, n, T, T, w.x, T, EPI_F32_RESID, w.x, T, skip, s));
-  EC_TRY(layernorm(w.x, T, b.ln2_g, b.ln2_b, w.ln, T, true, n, T, skip, s));
+  FusedLn ln2{b.ln2_g, b.ln2_b, fuse ? w.ln : nullptr, T, w.ln_cnt};
+  EC_TRY(linear(w.att, T, b.w_out, T, b.b_out, n, T, T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &ln2));
+  if (!fuse) EC_TRY(layernorm(w.x, T, b.ln2_g, b.ln2_b, w.ln, T, true, n, T, skip, s));
   EC_TRY(linear(w.ln, T, b.w_fc1, T, b.b_fc1, n, 4 * T, T, w.fc1, 4 * T, EPI_BF16_GELU, nullptr, 0, skip, s));
-  EC_TRY(linear(w.fc1, 4 * T, b.w_fc2, 4 * T, b.b_fc2, n, T, 4 * T, w.x, T, EPI_F32_RESID, w.x, T, skip, s));
+  FusedLn nxt{next_g, next_b, fuse ? w.ln : nullptr, T, w.ln_cnt};
+  EC_TRY(linear(w.fc1, 4 * T, b.w_fc2, 4 * T, b.b_fc2, n, T, 4 * T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &nxt));
   return EC_OK;
 }
 
-int Model::cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int n, cudaStream_t s) {
+int Model::cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int n, bool ln1_done, const float* next_g,
+                       const float* next_b, cudaStream_t s) {
   const int T = cfg.text_width, NK = cfg.n_queries - 1;
   const int* skip = &w.st->done;
-  EC_TRY(layernorm(w.x, T, b.ln1_g, b.ln1_b, w.ln, T, true, n, T, skip, s));
+  const bool fuse = decoder_fuse(n);
+  if (!ln1_done) EC_TRY(layernorm(w.x, T, b.ln1_g, b.ln1_b, w.ln, T, true, n, T, skip, s));
   EC_TRY(linear(w.ln, T, b.w_qkv, T, b.b_qkv, n, T, T, w.q, T, EPI_BF16, nullptr, 0, skip, s));   // q rows only
   EC_TRY(decode_cross_attention(w.q, kv, w.att, n, cfg.mm_heads, T / cfg.mm_heads, NK, w.finished, w.st, s));
-  EC_TRY(linear(w.att, T, b.w_out, T, b.b_out, n, T, T, w.x, T, EPI_F32_RESID, w.x, T, skip, s));
-  EC_TRY(layernorm(w.x, T, b.ln2_g, b.ln2_b, w.ln, T, true, n, T, skip, s));
+  FusedLn ln2{b.ln2_g, b.ln2_b, fuse ? w.ln : nullptr, T, w.ln_cnt};
+  EC_TRY(linear(w.att, T, b.w_out, T, b.b_out, n, T, T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &ln2));
+  if (!fuse) EC_TRY(layernorm(w.x, T, b.ln2_g, b.ln2_b, w.ln, T, true, n, T, skip, s));
   EC_TRY(linear(w.ln, T, b.w_fc1, T, b.b_fc1, n, 4 * T, T, w.fc1, 4 * T, EPI_BF16_GELU, nullptr, 0, skip, s));
-  EC_TRY(linear(w.fc1, 4 * T, b.w_fc2, 4 * T, b.b_fc2, n, T, 4 * T, w.x, T, EPI_F32_RESID, w.x, T, skip, s));
+  FusedLn nxt{next_g, next_b, fuse ? w.ln : nullptr, T, w.ln_cnt};
+  EC_TRY(linear(w.fc1, 4 * T, b.w_fc2, 4 * T, b.b_fc2, n, T, 4 * T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &nxt));
   return EC_OK;
 }
 
@@ -444,13 +485,23 @@ int Model::chain_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int 
                       float* logits, bool teacher_forced, cudaStream_t s) {
   const int T = cfg.text_width, V = cfg.vocab_size;
   EC_TRY(decode_embed(tokens, ld_tokens, tok_emb, txt_pos, w.x, n, T, w.st, s));
-  for (int l = 0; l < cfg.text_layers; ++l)
-    EC_TRY(self_block(tblocks[l], w, w.tk + l * w.cache_layer, w.tv + l * w.cache_layer, n, seq_len, cfg.text_heads, s));
-  for (int l = 0; l < cfg.mm_layers; ++l) {
-    EC_TRY(self_block(dself[l], w, w.dk + l * w.cache_layer, w.dv + l * w.cache_layer, n, seq_len, cfg.mm_heads, s));
-    EC_TRY(cross_block(dcross[l], w, w.cross_kv + l * w.cross_layer, n, s));
+  // block sequence: text tower, then (self, cross) pairs, then ln_final; each block's c_proj GEMM also produces the
+  // LayerNorm the NEXT block starts with (fused tail), so only the very first LayerNorm of the step is a launch
+  const bool fuse = decoder_fuse(n);
+  for (int l = 0; l < cfg.text_layers; ++l) {
+    const bool last_text = (l + 1 == cfg.text_layers);
+    const Block& nb = last_text ? dself[0] : tblocks[l + 1];
+    EC_TRY(self_block(tblocks[l], w, w.tk + l * w.cache_layer, w.tv + l * w.cache_layer, n, seq_len, cfg.text_heads,
+                      fuse && l > 0, nb.ln1_g, nb.ln1_b, s));
   }
-  EC_TRY(layernorm(w.x, T, ln_final_g, ln_final_b, w.ln, T, true, n, T, &w.st->done, s));
+  for (int l = 0; l < cfg.mm_layers; ++l) {
+    EC_TRY(self_block(dself[l], w, w.dk + l * w.cache_layer, w.dv + l * w.cache_layer, n, seq_len, cfg.mm_heads,
+                      fuse && (l > 0 || cfg.text_layers > 0), dcross[l].ln1_g, dcross[l].ln1_b, s));
+    const bool last = (l + 1 == cfg.mm_layers);
+    EC_TRY(cross_block(dcross[l], w, w.cross_kv + l * w.cross_layer, n, fuse, last ? ln_final_g : dself[l + 1].ln1_g,
+                       last ? ln_final_b : dself[l + 1].ln1_b, s));
+  }
+  if (!fuse) EC_TRY(layernorm(w.x, T, ln_final_g, ln_final_b, w.ln, T, true, n, T, &w.st->done, s));
   GemmArgs g{};
   g.A = w.ln; g.lda = T; g.W = w_vocab; g.ldw = T; g.M = n; g.N = V; g.K = T;
   g.logits = logits; g.ld_logits = V; g.logits_step_stride = (long long)n_total * V;

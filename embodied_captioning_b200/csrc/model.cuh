@@ -19,12 +19,16 @@ struct DecodeWs;
 struct GraphKey { const void* ws; const void* tokens; const void* logits; int n, seq_len, min_len, ld, tf, n_total; };
 
 constexpr int kMaxChains = 8;
+constexpr int kLnCountersEncoder = 4096;     // 128-row blocks of one image-tower call (1024 crops x 257 tokens = 2056)
+constexpr int kLnCountersPerChain = 64;      // 128-row blocks of one decoder chain
 
 struct Model {
   ec_config cfg;
   int device;
   bool finalized = false;
   bool use_graph = false;
+  bool fuse_ln = true;             // (ctor: off unless EC_FUSE_LN=1) LayerNorms computed by the residual GEMM's fused tail
+  int* ln_counters = nullptr;      // row-block arrival counters of the fused tails (zero between launches)
   bool use_tc_attention = false;   // tcgen05/TMEM attention for the ViT blocks (option "tc_attention")
   int patch_k = 0, patch_ld = 0;
 
@@ -57,6 +61,7 @@ struct Model {
 
   Model(const ec_config& c, int dev);
   ~Model();
+  bool decoder_fuse(int rows) const { return fuse_ln && ceil_div(rows, 128) <= kLnCountersPerChain; }
   int cfg_tokens() const { return (cfg.image_size / cfg.patch_size) * (cfg.image_size / cfg.patch_size) + 1; }
 
   int set_tensor(const char* name, const float* host, int64_t numel);
@@ -76,8 +81,10 @@ struct Model {
   int upload_bf16(const float* host, int rows, int cols, bool src_transposed, bf16** dst, int total_rows, int ld,
                   int row_off);
   int set_block_tensor(Block& b, int width, const char* leaf, const char* name, const float* h, int64_t numel);
-  int self_block(const Block& b, const DecodeWs& w, bf16* kc, bf16* vc, int n, int max_len, int heads, cudaStream_t s);
-  int cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int n, cudaStream_t s);
+  int self_block(const Block& b, const DecodeWs& w, bf16* kc, bf16* vc, int n, int max_len, int heads, bool ln1_done,
+                 const float* next_g, const float* next_b, cudaStream_t s);
+  int cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int n, bool ln1_done, const float* next_g,
+                  const float* next_b, cudaStream_t s);
   int chain_rows(int n) const;
   int chain_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len,
                  float* logits, bool teacher_forced, cudaStream_t s);

@@ -151,6 +151,13 @@ int ec_gemm_bf16(const void* a_bf16_dev, int32_t lda, const void* w_bf16_dev, in
                  int32_t k, const float* bias_dev, const float* residual_dev, int32_t ldr, void* out_dev, int32_t ldo,
                  int32_t epilogue /* 0 bf16, 1 bf16+gelu, 2 f32, 3 f32+residual */, int32_t use_simt_reference,
                  void* stream);
+/* residual GEMM (epilogue 3) that also writes ln_out_bf16[m, n] = LayerNorm(out rows; gamma, beta, eps 1e-5) as soon as
+ * a 128-row block of `out` is complete (the fused tail the model path uses for every LayerNorm but the first);
+ * ln_counters: >= ceil(m/128) int32, zero before the first call (re-armed by the kernel); n <= 1024. */
+int ec_gemm_bf16_ln(const void* a_bf16_dev, int32_t lda, const void* w_bf16_dev, int32_t ldw, int32_t m, int32_t n,
+                    int32_t k, const float* bias_dev, const float* residual_dev, int32_t ldr, float* out_dev, int32_t ldo,
+                    const float* ln_gamma_dev, const float* ln_beta_dev, void* ln_out_bf16_dev, int32_t ld_ln,
+                    int32_t* ln_counters_dev, void* stream);
 int ec_gemm_argmax(const void* a_bf16_dev, int32_t lda, const void* w_bf16_dev, int32_t ldw, int32_t m, int32_t n,
                    int32_t k, float* logits_dev /* nullable [m,n] */, int32_t* argmax_dev /* [m] */, void* ws_dev,
                    size_t ws_bytes, void* stream);

@@ -149,3 +149,30 @@ def test_attention_tcgen05_fused_qkv(device, B, H, S):
     rel_legacy = ((legacy.float() - ref).norm() / ref.norm()).item()
     print(f"tcgen05 attention B={B} H={H} S={S}: max err {err:.4f}, rel {rel:.2e} (mma.sync kernel rel {rel_legacy:.2e})")
     assert err < 0.03 and rel < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 768, 3072), (300, 768, 768), (20000, 1024, 1024), (33024, 1024, 4096), (129, 512, 256)])
+def test_gemm_fused_layernorm_tail(device, M, N, K):
+    """Residual GEMM that also emits LayerNorm(out) as bf16 once a 128-row block is complete (gemm_kernel.cuh::ln_tail):
+    `out` must be unchanged by the fusion and the bf16 rows must equal the stand-alone LayerNorm kernel bit for bit."""
+    from embodied_captioning_b200 import _native as nat
+    a = _rand_bf16((M, K), device, seed=11)
+    w = _rand_bf16((N, K), device, K ** -0.5, seed=12)
+    bias = torch.randn(N, device=device)
+    res = torch.randn(M, N, device=device) * 3
+    g = torch.randn(N, device=device) * 0.2 + 1.0
+    b = torch.randn(N, device=device) * 0.1
+    plain = ops.gemm(a, w, bias, ops.EPI_F32_RESID, residual=res)
+    ref_ln = ops.layernorm(plain, g, b, out_bf16=True)
+    out = torch.empty_like(plain)
+    ln = torch.zeros((M, N), device=device, dtype=torch.bfloat16)
+    cnt = torch.zeros(((M + 127) // 128,), device=device, dtype=torch.int32)
+    for _ in range(2):                                     # twice: the counters must re-arm themselves
+        ln.zero_()
+        nat.check(nat.lib().ec_gemm_bf16_ln(a.data_ptr(), K, w.data_ptr(), K, M, N, K, bias.data_ptr(), res.data_ptr(), N,
+                                            out.data_ptr(), N, g.data_ptr(), b.data_ptr(), ln.data_ptr(), N, cnt.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream), "ec_gemm_bf16_ln")
+        ops.check_watchdog(device)
+        assert torch.equal(out, plain)
+        assert torch.equal(ln, ref_ln)
+        assert int(cnt.abs().sum()) == 0
