@@ -76,6 +76,7 @@ static int launch_tile(const GemmArgs& a, cudaStream_t stream) {
   p.skip_flag = a.skip_flag;
   p.ln_g = a.ln_gamma; p.ln_b = a.ln_beta; p.ln_out = a.ln_out; p.ld_ln = a.ld_ln; p.ln_cnt = a.ln_counters;
   p.ln_tiles_n = ceil_div(a.N, BN);
+  p.pf_ptr = reinterpret_cast<const unsigned char*>(a.prefetch_ptr); p.pf_bytes = a.prefetch_bytes;
   const int tiles_m = ceil_div(a.M, kBM), tiles_n = ceil_div(a.N, BN);
   const int grid = std::min(tiles_m * tiles_n, num_sms());
   static bool attr_set = false;   // per template instantiation
@@ -104,6 +105,7 @@ static int launch_pair_ew(const GemmArgs& a, cudaStream_t stream) {
   p.skip_flag = a.skip_flag;
   p.ln_g = a.ln_gamma; p.ln_b = a.ln_beta; p.ln_out = a.ln_out; p.ld_ln = a.ld_ln; p.ln_cnt = a.ln_counters;
   p.ln_tiles_n = ceil_div(a.N, BN);
+  p.pf_ptr = nullptr; p.pf_bytes = 0;
   const int tiles_m = ceil_div(a.M, 2 * kBM), tiles_n = ceil_div(a.N, BN);
   const int clusters = std::min(tiles_m * tiles_n, num_sms() / 2);
   static bool attr_set = false;   // per template instantiation
@@ -271,6 +273,7 @@ int gemm_reference_simt(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream
   p.logits = a.logits; p.ld_logits = a.ld_logits; p.logits_step_stride = a.logits_step_stride; p.part_val = a.part_val; p.part_idx = a.part_idx;
   p.n_parts = a.n_parts; p.eos_col = a.eos_col; p.cur_len = a.cur_len; p.min_len = a.min_len; p.skip_flag = nullptr;
   p.ln_g = nullptr; p.ln_b = nullptr; p.ln_out = nullptr; p.ld_ln = 0; p.ln_cnt = nullptr; p.ln_tiles_n = 0;
+  p.pf_ptr = nullptr; p.pf_bytes = 0;
   dim3 grid(ceil_div(a.N, 128), a.M);
   gemm_simt_kernel<<<grid, 128, 0, stream>>>(a.A, a.lda, a.W, a.ldw, a.M, a.N, a.K, p, (int)epi);
   EC_POST_LAUNCH();

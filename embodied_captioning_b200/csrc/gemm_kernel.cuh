@@ -229,6 +229,9 @@ struct EpiParams {
   const int* skip_flag;
   // fused LayerNorm tail (EPI_F32_RESID only, ln_out != nullptr): see ln_tail()
   const float* ln_g; const float* ln_b; bf16* ln_out; int ld_ln; int* ln_cnt; int ln_tiles_n;
+  // L2 prefetch of the NEXT GEMM's weights (decoder steps: weights cycle through L2 once per step, so every K panel
+  // would otherwise arrive at HBM latency); issued by the otherwise idle warp 3
+  const unsigned char* pf_ptr; unsigned long long pf_bytes;
 };
 
 // One 32 x 32 chunk.  kFull = the whole chunk lies inside [M, N]: no per-element bound predicates (the interior
@@ -432,6 +435,17 @@ __device__ __forceinline__ void ln_tail(const EpiParams& p, int row_base, int e,
   }
 }
 
+// this CTA's share of [ptr, ptr + bytes) -> L2, 4 KB per bulk-prefetch instruction
+__device__ __forceinline__ void l2_prefetch_slice(const unsigned char* ptr, unsigned long long bytes, int lane) {
+  constexpr unsigned long long kChunk = 4096;
+  const unsigned long long n_chunks = (bytes + kChunk - 1) / kChunk;
+  for (unsigned long long c = (unsigned long long)blockIdx.x * 32 + lane; c < n_chunks; c += (unsigned long long)gridDim.x * 32) {
+    const unsigned long long off = c * kChunk;
+    const unsigned int sz = (unsigned int)((bytes - off < kChunk ? bytes - off : kChunk) & ~15ull);
+    if (sz) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr + off), "r"(sz) : "memory");
+  }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
@@ -488,6 +502,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (skip) {
     // fall through to the teardown
+  } else if (warp == 3) {
+    if (p.pf_ptr != nullptr) l2_prefetch_slice(p.pf_ptr, p.pf_bytes, lane);
   } else if (warp == 0) {
     // ===================================================================== TMA producer (warp-uniform loop, one
     // elected lane issues)

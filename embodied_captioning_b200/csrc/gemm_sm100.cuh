@@ -37,6 +37,8 @@ struct GemmArgs {
   // ln_out[M, N] (bf16) = LayerNorm(out rows; ln_gamma, ln_beta, eps 1e-5) once a 128-row block of `out` is complete.
   // ln_counters: >= ceil(M / 128) ints, zero before the first launch (the kernel re-arms them); N <= 1024, N % 4 == 0.
   const float* ln_gamma; const float* ln_beta; bf16* ln_out; int ld_ln; int* ln_counters;
+  // optional: bring [prefetch_ptr, +prefetch_bytes) into L2 while this GEMM runs (the next GEMM's weights; 1-CTA kernel)
+  const void* prefetch_ptr; size_t prefetch_bytes;
 };
 
 // number of arg-max partial slots per row produced by EPI_ARGMAX for vocabulary size N

@@ -70,6 +70,8 @@ Model::Model(const ec_config& c, int dev) : cfg(c), device(dev) {
   // 128-row block (latency-bound row loop on the GEMM's critical path) where the stand-alone kernel spreads the rows
   // over every SM at the HBM roofline, and every tile pays two named barriers + a device-scope fence + an atomic.
   // Encoder 180 -> 220 ms, decoder 113 -> 150 ms at 1024 crops.  Opt-in only (EC_FUSE_LN=1).
+  static const int env_pf = [] { const char* e = getenv("EC_PREFETCH_WEIGHTS"); return e ? atoi(e) : 1; }();
+  prefetch_weights = env_pf != 0;
   static const int env_fuse = [] { const char* e = getenv("EC_FUSE_LN"); return e ? atoi(e) : 0; }();
   if (env_fuse == 0) fuse_ln = false;
 }
@@ -243,12 +245,15 @@ struct FusedLn {      // LayerNorm applied to the rows of a residual GEMM's outp
   const float* g = nullptr; const float* b = nullptr; bf16* out = nullptr; int ld = 0; int* counters = nullptr;
 };
 
+struct Prefetch { const void* ptr = nullptr; size_t bytes = 0; };     // the next GEMM's weights -> L2
+
 static int linear(const bf16* A, int lda, const bf16* W, int ldw, const float* bias, int M, int N, int K, void* out,
                   int ldo, GemmEpilogue epi, const float* resid, int ldr, const int* skip, cudaStream_t s,
-                  const FusedLn* ln = nullptr) {
+                  const FusedLn* ln = nullptr, Prefetch pf = Prefetch()) {
   GemmArgs g{};
   g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.M = M; g.N = N; g.K = K; g.bias = bias;
   g.residual = resid; g.ldr = ldr; g.out = out; g.ldo = ldo; g.skip_flag = skip;
+  g.prefetch_ptr = pf.ptr; g.prefetch_bytes = pf.bytes;
   if (ln != nullptr && ln->out != nullptr) {
     g.ln_gamma = ln->g; g.ln_beta = ln->b; g.ln_out = ln->out; g.ld_ln = ln->ld; g.ln_counters = ln->counters;
   }
@@ -446,36 +451,49 @@ size_t Model::decode_workspace_bytes(int n, int seq_len) const {
 // `ln1_done`: w.ln already holds ln_1(x) (written by the previous block's fused tail); `next_g/next_b`: the LayerNorm
 // that follows this block (next block's ln_1 or ln_final), fused into c_proj when `fuse_ln` is on.
 int Model::self_block(const Block& b, const DecodeWs& w, bf16* kc, bf16* vc, int n, int max_len, int heads,
-                      bool ln1_done, const float* next_g, const float* next_b, cudaStream_t s) {
+                      bool ln1_done, const float* next_g, const float* next_b, Prefetch next_pf, cudaStream_t s) {
   const int T = cfg.text_width;
   const int* skip = &w.st->done;
   const bool fuse = decoder_fuse(n);
   if (!ln1_done) EC_TRY(layernorm(w.x, T, b.ln1_g, b.ln1_b, w.ln, T, true, n, T, skip, s));
-  EC_TRY(linear(w.ln, T, b.w_qkv, T, b.b_qkv, n, 3 * T, T, w.qkv, 3 * T, EPI_BF16, nullptr, 0, skip, s));
+  const size_t TT = (size_t)T * T * sizeof(bf16);
+  const Prefetch none;
+  // every GEMM pulls the next GEMM's weights into L2 (the 557 MB of decoder weights cycle through L2 once per step)
+  EC_TRY(linear(w.ln, T, b.w_qkv, T, b.b_qkv, n, 3 * T, T, w.qkv, 3 * T, EPI_BF16, nullptr, 0, skip, s, nullptr,
+                prefetch_weights ? Prefetch{b.w_out, TT} : none));
   EC_TRY(decode_self_attention(w.qkv, kc, vc, w.att, n, heads, T / heads, max_len, w.finished, w.st, s));
   FusedLn ln2{b.ln2_g, b.ln2_b, fuse ? w.ln : nullptr, T, w.ln_cnt};
-  EC_TRY(linear(w.att, T, b.w_out, T, b.b_out, n, T, T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &ln2));
+  EC_TRY(linear(w.att, T, b.w_out, T, b.b_out, n, T, T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &ln2,
+                prefetch_weights ? Prefetch{b.w_fc1, 4 * TT} : none));
   if (!fuse) EC_TRY(layernorm(w.x, T, b.ln2_g, b.ln2_b, w.ln, T, true, n, T, skip, s));
-  EC_TRY(linear(w.ln, T, b.w_fc1, T, b.b_fc1, n, 4 * T, T, w.fc1, 4 * T, EPI_BF16_GELU, nullptr, 0, skip, s));
+  EC_TRY(linear(w.ln, T, b.w_fc1, T, b.b_fc1, n, 4 * T, T, w.fc1, 4 * T, EPI_BF16_GELU, nullptr, 0, skip, s, nullptr,
+                prefetch_weights ? Prefetch{b.w_fc2, 4 * TT} : none));
   FusedLn nxt{next_g, next_b, fuse ? w.ln : nullptr, T, w.ln_cnt};
-  EC_TRY(linear(w.fc1, 4 * T, b.w_fc2, 4 * T, b.b_fc2, n, T, 4 * T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &nxt));
+  EC_TRY(linear(w.fc1, 4 * T, b.w_fc2, 4 * T, b.b_fc2, n, T, 4 * T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &nxt,
+                prefetch_weights ? next_pf : none));
   return EC_OK;
 }
 
 int Model::cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int n, bool ln1_done, const float* next_g,
-                       const float* next_b, cudaStream_t s) {
+                       const float* next_b, Prefetch next_pf, cudaStream_t s) {
   const int T = cfg.text_width, NK = cfg.n_queries - 1;
   const int* skip = &w.st->done;
   const bool fuse = decoder_fuse(n);
   if (!ln1_done) EC_TRY(layernorm(w.x, T, b.ln1_g, b.ln1_b, w.ln, T, true, n, T, skip, s));
-  EC_TRY(linear(w.ln, T, b.w_qkv, T, b.b_qkv, n, T, T, w.q, T, EPI_BF16, nullptr, 0, skip, s));   // q rows only
+  const size_t TT = (size_t)T * T * sizeof(bf16);
+  const Prefetch none;
+  EC_TRY(linear(w.ln, T, b.w_qkv, T, b.b_qkv, n, T, T, w.q, T, EPI_BF16, nullptr, 0, skip, s, nullptr,
+                prefetch_weights ? Prefetch{b.w_out, TT} : none));   // q rows only
   EC_TRY(decode_cross_attention(w.q, kv, w.att, n, cfg.mm_heads, T / cfg.mm_heads, NK, w.finished, w.st, s));
   FusedLn ln2{b.ln2_g, b.ln2_b, fuse ? w.ln : nullptr, T, w.ln_cnt};
-  EC_TRY(linear(w.att, T, b.w_out, T, b.b_out, n, T, T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &ln2));
+  EC_TRY(linear(w.att, T, b.w_out, T, b.b_out, n, T, T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &ln2,
+                prefetch_weights ? Prefetch{b.w_fc1, 4 * TT} : none));
   if (!fuse) EC_TRY(layernorm(w.x, T, b.ln2_g, b.ln2_b, w.ln, T, true, n, T, skip, s));
-  EC_TRY(linear(w.ln, T, b.w_fc1, T, b.b_fc1, n, 4 * T, T, w.fc1, 4 * T, EPI_BF16_GELU, nullptr, 0, skip, s));
+  EC_TRY(linear(w.ln, T, b.w_fc1, T, b.b_fc1, n, 4 * T, T, w.fc1, 4 * T, EPI_BF16_GELU, nullptr, 0, skip, s, nullptr,
+                prefetch_weights ? Prefetch{b.w_fc2, 4 * TT} : none));
   FusedLn nxt{next_g, next_b, fuse ? w.ln : nullptr, T, w.ln_cnt};
-  EC_TRY(linear(w.fc1, 4 * T, b.w_fc2, 4 * T, b.b_fc2, n, T, 4 * T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &nxt));
+  EC_TRY(linear(w.fc1, 4 * T, b.w_fc2, 4 * T, b.b_fc2, n, T, 4 * T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &nxt,
+                prefetch_weights ? next_pf : none));
   return EC_OK;
 }
 
@@ -492,14 +510,18 @@ int Model::chain_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int 
     const bool last_text = (l + 1 == cfg.text_layers);
     const Block& nb = last_text ? dself[0] : tblocks[l + 1];
     EC_TRY(self_block(tblocks[l], w, w.tk + l * w.cache_layer, w.tv + l * w.cache_layer, n, seq_len, cfg.text_heads,
-                      fuse && l > 0, nb.ln1_g, nb.ln1_b, s));
+                      fuse && l > 0, nb.ln1_g, nb.ln1_b, Prefetch{nb.w_qkv, 3 * (size_t)T * T * sizeof(bf16)}, s));
   }
   for (int l = 0; l < cfg.mm_layers; ++l) {
+    const size_t TTb = (size_t)T * T * sizeof(bf16);
     EC_TRY(self_block(dself[l], w, w.dk + l * w.cache_layer, w.dv + l * w.cache_layer, n, seq_len, cfg.mm_heads,
-                      fuse && (l > 0 || cfg.text_layers > 0), dcross[l].ln1_g, dcross[l].ln1_b, s));
+                      fuse && (l > 0 || cfg.text_layers > 0), dcross[l].ln1_g, dcross[l].ln1_b,
+                      Prefetch{dcross[l].w_qkv, TTb}, s));
     const bool last = (l + 1 == cfg.mm_layers);
     EC_TRY(cross_block(dcross[l], w, w.cross_kv + l * w.cross_layer, n, fuse, last ? ln_final_g : dself[l + 1].ln1_g,
-                       last ? ln_final_b : dself[l + 1].ln1_b, s));
+                       last ? ln_final_b : dself[l + 1].ln1_b,
+                       last ? Prefetch{tblocks.empty() ? nullptr : tblocks[0].w_qkv, 3 * TTb} : Prefetch{dself[l + 1].w_qkv, 3 * TTb},
+                       s));
   }
   if (!fuse) EC_TRY(layernorm(w.x, T, ln_final_g, ln_final_b, w.ln, T, true, n, T, &w.st->done, s));
   GemmArgs g{};

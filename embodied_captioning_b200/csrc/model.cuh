@@ -15,6 +15,7 @@ struct Block {   // one open_clip ResidualAttentionBlock
 };
 
 struct DecodeWs;
+struct Prefetch;
 
 struct GraphKey { const void* ws; const void* tokens; const void* logits; int n, seq_len, min_len, ld, tf, n_total; };
 
@@ -28,6 +29,7 @@ struct Model {
   bool finalized = false;
   bool use_graph = false;
   bool fuse_ln = true;             // (ctor: off unless EC_FUSE_LN=1) LayerNorms computed by the residual GEMM's fused tail
+  bool prefetch_weights = true;    // decoder GEMMs prefetch the next GEMM's weights into L2 (EC_PREFETCH_WEIGHTS=0: off)
   int* ln_counters = nullptr;      // row-block arrival counters of the fused tails (zero between launches)
   bool use_tc_attention = false;   // tcgen05/TMEM attention for the ViT blocks (option "tc_attention")
   int patch_k = 0, patch_ld = 0;
@@ -82,9 +84,9 @@ struct Model {
                   int row_off);
   int set_block_tensor(Block& b, int width, const char* leaf, const char* name, const float* h, int64_t numel);
   int self_block(const Block& b, const DecodeWs& w, bf16* kc, bf16* vc, int n, int max_len, int heads, bool ln1_done,
-                 const float* next_g, const float* next_b, cudaStream_t s);
+                 const float* next_g, const float* next_b, Prefetch next_pf, cudaStream_t s);
   int cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int n, bool ln1_done, const float* next_g,
-                  const float* next_b, cudaStream_t s);
+                  const float* next_b, Prefetch next_pf, cudaStream_t s);
   int chain_rows(int n) const;
   int chain_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len,
                  float* logits, bool teacher_forced, cudaStream_t s);
