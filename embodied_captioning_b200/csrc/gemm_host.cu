@@ -63,6 +63,13 @@ static int make_tmap(CUtensorMap* out, const bf16* base, int rows, int cols, int
 
 int gemm_argmax_parts(int N) { return ceil_div(N, 256) * 2; }
 
+static bool pair_shape(int M, int N) { return ceil_div(M, 2 * kBM) * ceil_div(N, 256) >= num_sms() / 2; }
+
+bool gemm_uses_pair_kernel(int M, int N) {
+  static const int mode = [] { const char* e = getenv("EC_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+  return mode != 0 && pair_shape(M, N);
+}
+
 template <int BN, int EPI>
 static int launch_tile(const GemmArgs& a, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
@@ -135,7 +142,7 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
 static bool use_pair_kernel(const GemmArgs& a) {
   static const int mode = [] { const char* e = getenv("EC_GEMM_PAIR"); return e ? atoi(e) : 1; }();
   if (mode == 0) return false;
-  return ceil_div(a.M, 2 * kBM) * ceil_div(a.N, 256) >= num_sms() / 2;
+  return pair_shape(a.M, a.N);
 }
 
 template <int EPI>

@@ -435,6 +435,60 @@ __device__ __forceinline__ void ln_tail(const EpiParams& p, int row_base, int e,
   }
 }
 
+// Same-CTA form of the tail (CTA-pair kernel): the tile schedule gives each cluster WHOLE row blocks (all n-tiles of a
+// 256-row block, consecutively), so the CTA that finishes the last n-tile wrote every column of its 128 rows itself:
+// no counter, no fence, no atomic -- one named barrier among the epilogue warps, then the stand-alone LayerNorm
+// arithmetic over rows that are still L2-hot, two rows per warp iteration so that the loads of a pair overlap.
+__device__ __forceinline__ void ln_tail_local(const EpiParams& p, int row_base, int e, int n_warps, int lane, int bar_id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(n_warps * 32) : "memory");
+  const int width = p.N, nvec = width >> 2;
+  for (int r = 2 * e; r < kBM; r += 2 * n_warps) {
+    const int row = row_base + r;
+    if (row >= p.M) break;
+    const bool two = (row + 1 < p.M);
+    const float* x0 = reinterpret_cast<const float*>(p.out) + (size_t)row * p.ldo;
+    const float* x1 = x0 + p.ldo;
+    float4 v0[kLnTailMaxVec], v1[kLnTailMaxVec];
+#pragma unroll
+    for (int i = 0; i < kLnTailMaxVec; ++i) {
+      const int c = lane + i * 32;
+      v0[i] = (c < nvec) ? ld_cg_f4(x0 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v1[i] = (c < nvec && two) ? ld_cg_f4(x1 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      float4 (&v)[kLnTailMaxVec] = h ? v1 : v0;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < kLnTailMaxVec; ++i)
+        if (lane + i * 32 < nvec) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      const float mean = warp_sum(s) / (float)width;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < kLnTailMaxVec; ++i) {
+        if (lane + i * 32 < nvec) {
+          const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+          q += (a * a + b * b) + (c * c + d * d);
+        }
+      }
+      const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)width + 1e-5f);      // same arithmetic as layernorm.cu
+      bf16* yr = p.ln_out + (size_t)(row + h) * p.ld_ln;
+#pragma unroll
+      for (int i = 0; i < kLnTailMaxVec; ++i) {
+        const int c = lane + i * 32;
+        if (c < nvec) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_g) + c), b = __ldg(reinterpret_cast<const float4*>(p.ln_b) + c);
+          uint2 pk;
+          pk.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+          pk.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+          reinterpret_cast<uint2*>(yr)[c] = pk;
+        }
+      }
+    }
+  }
+}
+
 // this CTA's share of [ptr, ptr + bytes) -> L2, 4 KB per bulk-prefetch instruction
 __device__ __forceinline__ void l2_prefetch_slice(const unsigned char* ptr, unsigned long long bytes, int lane) {
   constexpr unsigned long long kChunk = 4096;
@@ -656,6 +710,16 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int n_clusters = gridDim.x >> 1;
   const int num_tiles = tiles_m * tiles_n;               // 256-row tiles
   const int num_kb = (K + kBK - 1) / kBK;
+  // Tile schedule of this cluster: strided over the tile list, or -- with the fused LayerNorm tail -- a contiguous
+  // run of whole 256-row blocks (all their n-tiles), so that every row a CTA normalises was written by that CTA.
+  const bool contig = (EPI == EPI_F32_RESID) && (p.ln_out != nullptr);
+  int t_first = cluster_id, t_step = n_clusters, t_count = (num_tiles - cluster_id + n_clusters - 1) / n_clusters;
+  if (contig) {
+    const int mb_per = (tiles_m + n_clusters - 1) / n_clusters;
+    t_first = cluster_id * mb_per * tiles_n; t_step = 1;
+    t_count = max(0, min(mb_per * tiles_n, num_tiles - t_first));
+  }
+  if (t_count < 0) t_count = 0;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
@@ -692,7 +756,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // loop, one elected lane issues)
     {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+      for (int ti = 0, tile = t_first; ti < t_count; ++ti, tile += t_step) {
         const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
         const int a_row = m_blk * (2 * kBM) + (int)rank * kBM;
         const int b_row = n_blk * BN + (int)rank * (BN / 2);
@@ -717,7 +781,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const uint64_t adesc0 = make_smem_desc(smem_a0), bdesc0 = make_smem_desc(smem_b0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+      for (int ti = 0, tile = t_first; ti < t_count; ++ti, tile += t_step) {
         if (!bounded_wait(tempty_bar(acc), acc_phase ^ 1u, 2)) goto done;
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -750,7 +814,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     int acc = 0; uint32_t acc_phase = 0;
     int cur_len = 0;
     if (EPI == EPI_ARGMAX) cur_len = (p.cur_len != nullptr) ? *p.cur_len : (1 << 30);
-    for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+    for (int ti = 0, tile = t_first; ti < t_count; ++ti, tile += t_step) {
       const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
       if (!bounded_wait(tfull_bar(acc), acc_phase, 4)) break;
       ptx::tc_fence_after();
@@ -760,8 +824,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(tempty_bar(acc), 0));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      if (EPI == EPI_F32_RESID && p.ln_out != nullptr)
-        ln_tail(p, m_blk * (2 * kBM) + (int)rank * kBM, e, EW, lane, 1, reinterpret_cast<volatile int*>(tmem_slot_ptr + 1));
+      if (contig && n_blk == tiles_n - 1) ln_tail_local(p, m_blk * (2 * kBM) + (int)rank * kBM, e, EW, lane, 1);
     }
     pdl_trigger_bottom();
   }

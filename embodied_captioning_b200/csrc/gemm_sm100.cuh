@@ -41,6 +41,9 @@ struct GemmArgs {
   const void* prefetch_ptr; size_t prefetch_bytes;
 };
 
+// true when gemm_bf16 runs this shape on the CTA-pair kernel (whose fused LayerNorm tail needs no inter-CTA sync)
+bool gemm_uses_pair_kernel(int M, int N);
+
 // number of arg-max partial slots per row produced by EPI_ARGMAX for vocabulary size N
 int gemm_argmax_parts(int N);
 

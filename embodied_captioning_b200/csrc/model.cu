@@ -74,6 +74,10 @@ Model::Model(const ec_config& c, int dev) : cfg(c), device(dev) {
   prefetch_weights = env_pf != 0;
   static const int env_fuse = [] { const char* e = getenv("EC_FUSE_LN"); return e ? atoi(e) : 0; }();
   if (env_fuse == 0) fuse_ln = false;
+  // image tower: the CTA-local tail (no atomics, contiguous tile schedule) also loses -- the epilogue warps that run it
+  // delay the next tile's accumulator drain (bench 318.0 vs 302.9 ms/step) -> opt-in as well (EC_FUSE_LN_ENC=1)
+  static const int env_fuse_enc = [] { const char* e = getenv("EC_FUSE_LN_ENC"); return e ? atoi(e) : 0; }();
+  fuse_ln_encoder = env_fuse_enc != 0 && ln_counters != nullptr;
 }
 
 Model::~Model() {
@@ -333,7 +337,8 @@ int Model::encode_image(const bf16* x, int n, float* latent, float* embs, void* 
                 nullptr, s));
   EC_TRY(vision_embed_ln_pre(w.patch_emb, cls_emb, vis_pos, ln_pre_g, ln_pre_b, w.resid, n, TV, W, s));
   // Every LayerNorm except the first is computed by the residual GEMM that completes its input rows (fused tail).
-  const bool fuse = fuse_ln && ceil_div(Mv, 128) <= kLnCountersEncoder;
+  // fused only on the CTA-pair kernel, whose tail is local to one CTA (the 1-CTA kernel's atomic form is slower)
+  const bool fuse = fuse_ln_encoder && gemm_uses_pair_kernel(Mv, W) && ceil_div(Mv, 128) <= kLnCountersEncoder;
   for (int l = 0; l < cfg.vision_layers; ++l) {
     const Block& b = vblocks[l];
     if (l == 0 || !fuse) EC_TRY(layernorm(w.resid, W, b.ln1_g, b.ln1_b, w.ln, W, true, Mv, W, nullptr, s));

@@ -29,6 +29,7 @@ struct Model {
   bool finalized = false;
   bool use_graph = false;
   bool fuse_ln = true;             // (ctor: off unless EC_FUSE_LN=1) LayerNorms computed by the residual GEMM's fused tail
+  bool fuse_ln_encoder = false;    // image tower: LayerNorm tails inside the CTA-pair residual GEMMs (EC_FUSE_LN_ENC=1: on; measured slower)
   bool prefetch_weights = true;    // decoder GEMMs prefetch the next GEMM's weights into L2 (EC_PREFETCH_WEIGHTS=0: off)
   int* ln_counters = nullptr;      // row-block arrival counters of the fused tails (zero between launches)
   bool use_tc_attention = false;   // tcgen05/TMEM attention for the ViT blocks (option "tc_attention")
