@@ -47,7 +47,7 @@ def main():
     ev1.record()
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
-    print("profiled stage", args.stage, "batch", args.batch, "graph", args.graph, "PDL", os.environ.get("EC_PDL", "1"),
+    print("profiled stage", args.stage, "batch", args.batch, "graph", args.graph, "PDL", os.environ.get("EC_PDL", "0"),
           "ms", round(ev0.elapsed_time(ev1), 3))
 
 
