@@ -169,7 +169,10 @@ static int launch_attn(const AttnArgs& a, cudaStream_t stream) {
   const int skv_pad = ceil_div(a.skv, kKvChunk) * kKvChunk;
   const size_t smem = (size_t)2 * skv_pad * (D + 8) * sizeof(bf16);
   EC_REQUIRE(smem <= 220 * 1024, EC_ERR_UNSUPPORTED, "attention: %d keys x head_dim %d exceed shared memory", a.skv, D);
-  static size_t configured = 0;
+  static size_t configured_dev[64] = {};
+  const int dev_ = current_device();
+  EC_REQUIRE(dev_ >= 0, EC_ERR_DEVICE, "no current CUDA device");
+  size_t& configured = configured_dev[dev_];
   if (smem > configured) {
     EC_CHECK_CUDA(cudaFuncSetAttribute(attention_full_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

@@ -541,7 +541,10 @@ int attention_sm100_fused_qkv(const bf16* qkv, long long ld, int q_col0, int k_c
   CUtensorMap tm128, tm16;
   EC_TRY(encode_map(&tm128, qkv, rows, cols, ld, kATile));
   EC_TRY(encode_map(&tm16, qkv, rows, cols, ld, kAKeysTail));
-  static bool attr = false;
+  static bool attr_done[64] = {};
+  const int dev_ = current_device();
+  EC_REQUIRE(dev_ >= 0, EC_ERR_DEVICE, "no current CUDA device");
+  bool& attr = attr_done[dev_];
   if (!attr) {
     EC_CHECK_CUDA(cudaFuncSetAttribute(attention_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kASmemBytes));
     EC_CHECK_CUDA(cudaFuncSetAttribute(attention_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kASmemBytes));

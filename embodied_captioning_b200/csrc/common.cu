@@ -29,6 +29,11 @@ bool pdl_enabled() {
   return v == 1;
 }
 
+int current_device() {
+  int dev = 0;
+  return (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) ? dev : -1;
+}
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;

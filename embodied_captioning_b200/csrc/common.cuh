@@ -39,6 +39,7 @@ const char* last_error();
   } while (0)
 
 int num_sms();
+int current_device();     // cudaGetDevice, -1 on error (kernel attributes such as the dynamic smem limit are per device)
 
 // kernel-launch accounting (bench.py reports how many of our kernels ran inside the timed region)
 void note_launches(long long n);

@@ -86,7 +86,10 @@ static int launch_tile(const GemmArgs& a, cudaStream_t stream) {
   p.pf_ptr = reinterpret_cast<const unsigned char*>(a.prefetch_ptr); p.pf_bytes = a.prefetch_bytes;
   const int tiles_m = ceil_div(a.M, kBM), tiles_n = ceil_div(a.N, BN);
   const int grid = std::min(tiles_m * tiles_n, num_sms());
-  static bool attr_set = false;   // per template instantiation
+  static bool attr_done[64] = {};   // per template instantiation and device
+  const int dev_ = current_device();
+  EC_REQUIRE(dev_ >= 0, EC_ERR_DEVICE, "no current CUDA device");
+  bool& attr_set = attr_done[dev_];
   if (!attr_set) {
     EC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
@@ -115,7 +118,10 @@ static int launch_pair_ew(const GemmArgs& a, cudaStream_t stream) {
   p.pf_ptr = nullptr; p.pf_bytes = 0;
   const int tiles_m = ceil_div(a.M, 2 * kBM), tiles_n = ceil_div(a.N, BN);
   const int clusters = std::min(tiles_m * tiles_n, num_sms() / 2);
-  static bool attr_set = false;   // per template instantiation
+  static bool attr_done[64] = {};   // per template instantiation and device
+  const int dev_ = current_device();
+  EC_REQUIRE(dev_ >= 0, EC_ERR_DEVICE, "no current CUDA device");
+  bool& attr_set = attr_done[dev_];
   if (!attr_set) {
     EC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<BN, EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kSmem));

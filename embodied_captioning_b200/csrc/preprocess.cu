@@ -218,7 +218,10 @@ int preprocess_crops(const unsigned char* frames, int n_frames, int frame_h, int
   const int max_strip_rows = (int)(kBandRows * s_max + 4.0 * s_max) + 4;
   const size_t smem = (size_t)(size * kMaxTaps + 2 * size + kBandRows * kMaxTaps + 2 * kBandRows) * sizeof(int) +
                       (size_t)max_strip_rows * size * 3;
-  static size_t configured = 0;
+  static size_t configured_dev[64] = {};
+  const int dev_ = current_device();
+  EC_REQUIRE(dev_ >= 0, EC_ERR_DEVICE, "no current CUDA device");
+  size_t& configured = configured_dev[dev_];
   if (smem > configured) {
     EC_CHECK_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
