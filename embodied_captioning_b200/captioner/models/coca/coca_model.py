@@ -143,6 +143,8 @@ class CoCa(nn.Module):
         if strict and (missing or unexpected):
             raise RuntimeError(f"Error(s) in loading state_dict for CoCa: missing keys {missing[:8]}"
                                f"{'...' if len(missing) > 8 else ''}, unexpected keys {unexpected[:8]}")
+        if self._loaded:
+            self._release()       # a finalized native model may be sealed (LayerNorm folded into its weights): start over
         self._ensure_handle()
         lib = nat.lib()
         with torch.cuda.device(self._device):

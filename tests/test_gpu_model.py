@@ -195,8 +195,11 @@ def test_early_eos_and_padding_protocol(device):
     model = CoCa(cfg, device=device)
     model.load_state_dict(sd)
     out = model.generate(x.to(device), generation_type="top_k", seq_len=20)
-    ref = OracleCoCa(cfg, sd).generate(images=x, seq_len=20, mode="kvcache")
-    assert torch.equal(out["text"].cpu(), ref["text"])
+    orc = OracleCoCa(cfg, sd)
+    _, embs_ref = orc.encode_image_tokens(x)
+    ref = orc.generate(image_embs=embs_ref, seq_len=20, mode="kvcache")
+    # tokens 1..4 come from near-uniform random-init logits: identical, or split at a proven fp32 near-tie
+    _check_tokens(cfg, orc, embs_ref, out["text"].cpu(), ref, 20)
     assert out["text"].shape[1] == 6 and (out["text"][:, 5] == cfg.eos_token_id).all()
     assert len(out["logits"]) == 5
     full = model.generate(x.to(device), generation_type="top_k", seq_len=20, fixed_output_length=True)["text"]
