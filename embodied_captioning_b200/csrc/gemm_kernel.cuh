@@ -1,10 +1,15 @@
-// Device side of the tcgen05 / TMEM / TMA GEMM (sm_100a).  See gemm_sm100.cuh for the contract.
+// Device side of the tcgen05 / TMEM / TMA GEMMs (sm_100a).  See gemm_sm100.cuh for the contract.
 //
+// Two kernels share the epilogue code:
+//   gemm_tcgen05_pair_kernel  CTA pairs (cluster of 2), tcgen05.mma.cta_group::2, UMMA 256 x 256 x 16: the large GEMMs
+//   gemm_tcgen05_kernel       one CTA per tile, cta_group::1, UMMA 128 x BN x 16: small-M GEMMs (decoder steps, pooler)
+// Warp roles in both:
 //   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx)
-//   warp 1      : MMA issuer     (one thread: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16, fp32 accum in TMEM)
+//   warp 1      : MMA issuer     (warp-uniform loop, one elected lane issues tcgen05.mma / tcgen05.commit)
 //   warp 2      : TMEM allocator
-//   warps 4..11 : epilogue       (tcgen05.ld 32x32b -> bias / GELU / arg-max in registers -> per-warp swizzled
-//                                 shared-memory transpose -> fully coalesced 128-byte global rows)
+//   warp 3      : L2 prefetch of the next GEMM's weights (decoder steps), otherwise idle
+//   warps 4..   : 8 or 16 epilogue warps (tcgen05.ld 32x32b -> bias / GELU / residual / arg-max in registers ->
+//                 per-warp swizzled shared-memory transpose -> coalesced global row segments)
 // Persistent CTAs (1 per SM) walk the tile list; two TMEM accumulator stages overlap epilogue(i) with mainloop(i+1).
 #pragma once
 #include "gemm_sm100.cuh"

@@ -1,11 +1,12 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
 //
 // A (activations) and W (nn.Linear weight layout, open_clip `in_proj_weight` / `c_fc.weight` ...) are
-// both K-major bf16, staged by TMA into 128B-swizzled shared-memory tiles and consumed by
-// tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BN x 16) with fp32 accumulators in TMEM.
-// Persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer,
-// warp 2 = TMEM allocator, warps 4..11 = epilogue (TMEM -> registers -> global).  Two TMEM
-// accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+// both K-major bf16, staged by TMA into 128B-swizzled shared-memory tiles and consumed by tcgen05.mma with fp32
+// accumulators in TMEM: CTA pairs with cta_group::2 (UMMA 256 x 256 x 16) when the problem has at least one
+// 256 x 256 tile per SM pair, otherwise cta_group::1 (UMMA 128 x BN x 16).  Persistent CTAs (one per SM),
+// warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4.. = epilogue
+// (TMEM -> registers -> global).  Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of
+// tile i+1.
 #pragma once
 #include "common.cuh"
 
