@@ -158,9 +158,39 @@ __global__ void __launch_bounds__(256) im2col_kernel(const bf16* __restrict__ im
   }
 }
 
+// two pixels (one 32-bit word) per thread: patch rows are runs of `patch` contiguous pixels in both layouts and every
+// offset is even when `patch` and `ld` are
+__global__ void __launch_bounds__(256) im2col_x2_kernel(const uint32_t* __restrict__ img, uint32_t* __restrict__ out, int n,
+                                                        int size, int patch, int ld) {
+  const int grid_w = size / patch;
+  const int hp = patch >> 1;                      // words per patch row
+  const int kwords = 3 * patch * hp;              // words per output row
+  const long long total = (long long)n * grid_w * grid_w * kwords;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int kw = (int)(i % kwords);
+    const long long prow = i / kwords;
+    const int pidx = (int)(prow % (grid_w * grid_w));
+    const int b = (int)(prow / (grid_w * grid_w));
+    const int c = kw / (patch * hp), rem = kw % (patch * hp);
+    const int py = rem / hp, pw = rem % hp;
+    const int gy = pidx / grid_w, gx = pidx % grid_w;
+    out[(prow * ld) / 2 + kw] = img[((((size_t)b * 3 + c) * size + (gy * patch + py)) * size + gx * patch) / 2 + pw];
+  }
+}
+
 int im2col_patches(const bf16* img, bf16* out, int n, int size, int patch, int ld, cudaStream_t stream) {
   EC_REQUIRE(size % patch == 0 && ld >= 3 * patch * patch, EC_ERR_INVALID, "im2col: bad geometry");
   if (n <= 0) return EC_OK;
+  if (patch % 2 == 0 && ld % 2 == 0 && size % 2 == 0 && (reinterpret_cast<uintptr_t>(img) & 3u) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
+    const long long words = (long long)n * (size / patch) * (size / patch) * 3 * patch * (patch / 2);
+    const int grid2 = (int)std::min<long long>(ceil_div<long long>(words, 256), (long long)num_sms() * 16);
+    im2col_x2_kernel<<<grid2, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(img), reinterpret_cast<uint32_t*>(out), n,
+                                                size, patch, ld);
+    EC_POST_LAUNCH();
+    return EC_OK;
+  }
   const long long total = (long long)n * (size / patch) * (size / patch) * 3 * patch * patch;
   const int grid = (int)std::min<long long>(ceil_div<long long>(total, 256), (long long)num_sms() * 16);
   im2col_kernel<<<grid, 256, 0, stream>>>(img, out, n, size, patch, ld);
