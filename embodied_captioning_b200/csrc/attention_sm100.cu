@@ -217,7 +217,7 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       aptx::mbar_init(BAR(KV_FULL, i), 1);
-      aptx::mbar_init(BAR(KV_EMPTY, i), 1);           // commit after the last PV of the pair
+      aptx::mbar_init(BAR(KV_EMPTY, i), n_qtiles);    // one commit per PV of the pair (each issued by its softmax group)
       aptx::mbar_init(BAR(Q_FULL, i), 1);
       aptx::mbar_init(BAR(Q_EMPTY, i), n_tail > 0 ? 1 + 128 : 1);   // QK^T commit (+ the row threads' tail-key dots)
       aptx::mbar_init(BAR(S_FULL, i), 1);
@@ -269,28 +269,11 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer (warp-uniform loop, one elected lane
-    // issues the 4 + 16 tcgen05.mma of a tile back to back)
+    // ============================================================ QK^T issuer (warp-uniform loop, one elected lane).
+    // The P.V MMAs of a tile are issued by the tile's own softmax group (one handoff less in the per-tile chain).
     {
-      const uint32_t id_qk = idesc_qk(n_mma), id_pv = idesc_pv();
+      const uint32_t id_qk = idesc_qk(n_mma);
       uint32_t kv_it = 0, it = 0;            // `it` counts q tiles globally: buffers alternate with it & 1
-      int prev_valid = 0; uint32_t prev_it = 0; int prev_kvb = 0; bool prev_last = false;
-      auto issue_pv = [&](uint32_t pit, int pkvb, bool last_of_pair) -> bool {
-        const int sb = pit & 1;
-        if (!await(BAR(P_READY, sb), (pit >> 1) & 1, 5)) return false;
-        aptx::tc_fence_after();
-        const uint32_t t_p = tmem_base + (uint32_t)(sb * 256);
-        const uint32_t t_o = t_p + 128;
-        const uint64_t vdesc0 = desc_mnmajor(v_smem(pkvb));
-        if (aptx::elect_one()) {
-          for (int k = 0; k < n_mma / 16; ++k)
-            aptx::umma_ts(t_o, t_p + (uint32_t)(k * 8), vdesc0 + (uint64_t)(k * (2048 >> 4)), id_pv, k > 0 ? 1u : 0u);
-          aptx::umma_commit(BAR(O_FULL, sb));
-          if (last_of_pair) aptx::umma_commit(BAR(KV_EMPTY, pkvb));
-        }
-        __syncwarp();
-        return true;
-      };
       for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         const int kvb = kv_it & 1;
         if (!await(BAR(KV_FULL, kvb), (kv_it >> 1) & 1, 3)) goto done;
@@ -309,12 +292,9 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
             aptx::umma_commit(BAR(Q_EMPTY, sb));
           }
           __syncwarp();
-          if (prev_valid) { if (!issue_pv(prev_it, prev_kvb, prev_last)) goto done; }
-          prev_valid = 1; prev_it = it; prev_kvb = kvb; prev_last = (t == n_qtiles - 1);
         }
         ++kv_it;
       }
-      if (prev_valid) issue_pv(prev_it, prev_kvb, prev_last);
     }
   } else if (warp >= 4) {
     // ============================================================ softmax + epilogue (one thread per query row)
@@ -323,6 +303,24 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
     const int r = quad * 32 + lane;           // row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     uint32_t kv_it = 0, it = 0;
+    const uint32_t id_pv = idesc_pv();
+    // all 128 rows of P are in TMEM -> the group's first warp issues O = P V and publishes O_FULL / frees K,V
+    auto group_issue_pv = [&](int sb, int kvb) {
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      if (quad == 0) {
+        aptx::tc_fence_after();
+        const uint32_t t_p = tmem_base + (uint32_t)(sb * 256);
+        const uint32_t t_o = t_p + 128;
+        const uint64_t vdesc0 = desc_mnmajor(v_smem(kvb));
+        if (aptx::elect_one()) {
+          for (int k = 0; k < n_mma / 16; ++k)
+            aptx::umma_ts(t_o, t_p + (uint32_t)(k * 8), vdesc0 + (uint64_t)(k * (2048 >> 4)), id_pv, k > 0 ? 1u : 0u);
+          aptx::umma_commit(BAR(O_FULL, sb));
+          aptx::umma_commit(BAR(KV_EMPTY, kvb));
+        }
+        __syncwarp();
+      }
+    };
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++kv_it) {
       const int b = pair / a.heads, h = pair % a.heads;
       const int kvb = kv_it & 1;
@@ -341,7 +339,7 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
             aptx::mbar_arrive(BAR(Q_EMPTY, sb));
           }
           if (!await(BAR(S_FULL, sb), par, 9)) goto done;
-          aptx::mbar_arrive(BAR(P_READY, sb));
+          group_issue_pv(sb, kvb);
           if (!await(BAR(O_FULL, sb), par, 10)) goto done;
           aptx::mbar_arrive(BAR(S_EMPTY, sb));
           continue;
@@ -461,7 +459,7 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
         }
         aptx::tmem_st_wait();
         aptx::tc_fence_before();
-        aptx::mbar_arrive(BAR(P_READY, sb));
+        group_issue_pv(sb, kvb);
         // ---- O ready
         if (!await(BAR(O_FULL, sb), par, 10)) goto done;
         aptx::tc_fence_after();
