@@ -176,6 +176,11 @@ constexpr int kFirstEpiWarp = 4;
 constexpr int kThreads = (kFirstEpiWarp + kEpiWarps) * 32;   // 384
 constexpr int kEpiStageBytes = 32 * 32 * 4;                  // one 32x32 fp32 chunk per epilogue warp
 constexpr long long kWatchdogCycles = 4000000000LL;          // ~2 s at 2 GHz
+#ifdef EC_NO_DUAL_ISSUE
+constexpr bool kDualIssue = false;
+#else
+constexpr bool kDualIssue = true;
+#endif
 
 template <int BN> struct TileCfg {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
@@ -243,7 +248,8 @@ struct EpiParams {
 // of the matrix, i.e. nearly every chunk; they were a third of the epilogue's instructions).
 template <int BN, int EPI, bool kFull>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, uint32_t taddr, int row0, int gcol0, int lane,
-                                               uint32_t stg, int cur_len, float& best_v, int& best_i) {
+                                               uint32_t stg, int cur_len, float& best_v, int& best_i,
+                                               uint32_t acc2_off = 0) {
   const int cc = lane & 7;
   const int gcol = gcol0 + cc * 4;
   // The residual may alias the output (in-place residual stream): every element is read and written by the same
@@ -265,6 +271,12 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, uint32_t tadd
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (acc2_off != 0) {      // dual-issuer mode: the odd k-blocks were accumulated in the second TMEM stage
+    ptx::tmem_ld_32x32(taddr + acc2_off, r);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+  }
   if (p.bias != nullptr) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -349,7 +361,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, uint32_t tadd
 // shared-memory transpose -> coalesced global row segments.  `row0` = first global row of the slab.
 template <int BN, int EPI, int PARTS = 2>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_acc, int row0, int n_blk, int quad,
-                                              int half, int lane, uint32_t stg, int cur_len) {
+                                              int half, int lane, uint32_t stg, int cur_len, uint32_t acc2_off = 0) {
   static_assert(EPI != EPI_ARGMAX || PARTS == 2, "arg-max partial slots are laid out for two column halves");
   constexpr int kColsPerWarp = BN / PARTS;
   constexpr int kChunks = kColsPerWarp / 32;
@@ -362,9 +374,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
     const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)col_in_tile;
     if (gcol0 >= p.N) continue;           // warp-uniform: nothing of this chunk is inside the matrix
     if (rows_full && gcol0 + 32 <= p.N)
-      epilogue_chunk<BN, EPI, true>(p, taddr, row0, gcol0, lane, stg, cur_len, best_v, best_i);
+      epilogue_chunk<BN, EPI, true>(p, taddr, row0, gcol0, lane, stg, cur_len, best_v, best_i, acc2_off);
     else
-      epilogue_chunk<BN, EPI, false>(p, taddr, row0, gcol0, lane, stg, cur_len, best_v, best_i);
+      epilogue_chunk<BN, EPI, false>(p, taddr, row0, gcol0, lane, stg, cur_len, best_v, best_i, acc2_off);
   }
   if (EPI == EPI_ARGMAX && row0 + lane < p.M) {
     const size_t slot = (size_t)(row0 + lane) * p.n_parts + (size_t)(n_blk * 2 + half);
@@ -558,11 +570,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   pdl_wait();     // from here on we touch memory written by the previous kernel
   const bool skip = (p.skip_flag != nullptr && *p.skip_flag != 0);
+  // Dual-issuer mode (one tile per CTA, i.e. the small-M GEMMs of the decoder steps).  Measured: the K loop of a
+  // lone CTA costs ~0.3 us per k-block whatever the ring depth or the tile width (scripts/ingest_*_probe.py) -- the
+  // time ONE thread needs to issue four tcgen05.mma + a commit -- so K = 3072 is 14 us however few rows there are.
+  // Warp 3 becomes a second issuer: warp 1 takes the even k-blocks into accumulator stage 0, warp 3 the odd ones
+  // into stage 1, and the epilogue adds the two stages (fixed assignment: bit-reproducible).
+  const bool dual = (num_tiles <= (int)gridDim.x) && (num_kb >= 2) && kDualIssue;
 
   if (skip) {
     // fall through to the teardown
-  } else if (warp == 3) {
+  } else if (warp == 2) {
     if (p.pf_ptr != nullptr) l2_prefetch_slice(p.pf_ptr, p.pf_bytes, lane);
+  } else if (warp == 3 || (warp == 1 && dual)) {
+    if (dual && blockIdx.x < num_tiles) {
+      const int w = (warp == 1) ? 0 : 1;
+      constexpr uint32_t idesc = make_idesc<BN>();
+      const uint64_t adesc0 = make_smem_desc(smem_a0), bdesc0 = make_smem_desc(smem_b0);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(w * BN);
+      for (int kb = w; kb < num_kb; kb += 2) {
+        const int stage = kb % Cfg::kStages;
+        const uint32_t phase = (uint32_t)((kb / Cfg::kStages) & 1);
+        if (!bounded_wait(full_bar(stage), phase, 3)) goto done;
+        ptx::tc_fence_after();
+        const uint64_t adesc = adesc0 + (uint64_t)((stage * Cfg::kABytes) >> 4);
+        const uint64_t bdesc = bdesc0 + (uint64_t)((stage * Cfg::kBBytes) >> 4);
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            ptx::umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb > w || k > 0) ? 1u : 0u);
+          ptx::umma_commit(empty_bar(stage));
+        }
+        __syncwarp();
+      }
+      if (ptx::elect_one()) ptx::umma_commit(tfull_bar(w));
+      __syncwarp();
+    }
   } else if (warp == 0) {
     // ===================================================================== TMA producer (warp-uniform loop, one
     // elected lane issues)
@@ -631,9 +673,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
       if (!bounded_wait(tfull_bar(acc), acc_phase, 4)) break;
+      if (dual && !bounded_wait(tfull_bar(1), 0u, 4)) break;      // second issuer's accumulator (stage 1)
       ptx::tc_fence_after();
       epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m_blk * kBM + quad * 32, n_blk, quad, half, lane, stg,
-                             cur_len);
+                             cur_len, dual ? (uint32_t)BN : 0u);
       // release the accumulator stage back to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
