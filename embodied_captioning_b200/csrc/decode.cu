@@ -139,13 +139,15 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __res
   constexpr int D = 64;
   pdl_trigger_top();
   pdl_wait();
-  if (st->done) return;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x * 4 + w;
   if (pair >= batch * heads) return;
   const int b = pair / heads, h = pair % heads;
-  if (finished[b]) return;
-  const int pos = st->cur_len - 1;
+  // the three control words in ONE round trip (as dependent early-outs they were three L2 latencies in a row)
+  const int done = st->done, cur_len = st->cur_len;
+  const unsigned char fin = finished[b];
+  if (done || fin) return;
+  const int pos = cur_len - 1;
   const int C = heads * D;
   const int sub = lane & 7, grp = lane >> 3;
   const bf16* row = qkv + (size_t)b * 3 * C + h * D + sub * 8;
@@ -181,16 +183,17 @@ __global__ void __launch_bounds__(128) decode_cross_attn_kernel(const bf16* __re
   constexpr int D = 64;
   pdl_trigger_top();
   pdl_wait();
-  if (st->done) return;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x * 4 + w;
   if (pair >= batch * heads) return;
   const int b = pair / heads, h = pair % heads;
-  if (finished[b]) return;
   const int C = heads * D;
   const int sub = lane & 7;
+  const int done = st->done;                 // control words and the query slice in one round trip
+  const unsigned char fin = finished[b];
   float qf[8];
   load_q_slice(q + (size_t)b * C + h * D + sub * 8, qf);
+  if (done || fin) return;
   const bf16* kbase = kv + (size_t)b * n_kv * 2 * C + h * D + sub * 8;
   float acc[8], inv;
   warp_attend(qf, kbase, kbase + C, (size_t)2 * C, n_kv, lane, acc, inv);

@@ -96,7 +96,7 @@ static int launch_tile(const GemmArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   note_launches(1);
-  EC_CHECK_CUDA(launch_kernel(gemm_tcgen05_kernel<BN, EPI>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, stream,
+  EC_CHECK_CUDA(launch_kernel(gemm_tcgen05_kernel<BN, EPI>, dim3(grid), dim3(kThreads1), (size_t)Cfg::kSmemBytes, stream,
                               ta, tw, p, a.K, tiles_m, tiles_n));
   return EC_OK;
 }

@@ -174,6 +174,8 @@ constexpr int kUmmaK = 16;
 constexpr int kEpiWarps = 8;        // two warps per TMEM lane quadrant (column halves)
 constexpr int kFirstEpiWarp = 4;
 constexpr int kThreads = (kFirstEpiWarp + kEpiWarps) * 32;   // 384
+constexpr int kSecondProducerWarp = kFirstEpiWarp + kEpiWarps;   // 1-CTA kernel only: warp 12 loads the odd k-blocks
+constexpr int kThreads1 = kThreads + 32;                          // 416
 constexpr int kEpiStageBytes = 32 * 32 * 4;                  // one 32x32 fp32 chunk per epilogue warp
 constexpr long long kWatchdogCycles = 4000000000LL;          // ~2 s at 2 GHz
 #ifdef EC_NO_DUAL_ISSUE
@@ -518,11 +520,16 @@ __device__ __forceinline__ void l2_prefetch_slice(const unsigned char* ptr, unsi
 }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads1, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     EpiParams p, int K, int tiles_m, int tiles_n) {
   using Cfg = TileCfg<BN>;
   pdl_trigger_top();
+  // The dependency wait comes first: without programmatic dependent launch (the default -- it measured slower inside
+  // the step graphs) it is a no-op, and the skip flag's L2 round trip then overlaps the prologue instead of
+  // sitting between it and the first TMA load of a 6 us kernel.
+  pdl_wait();
+  const int skip_word = (p.skip_flag != nullptr) ? *p.skip_flag : 0;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -568,8 +575,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  pdl_wait();     // from here on we touch memory written by the previous kernel
-  const bool skip = (p.skip_flag != nullptr && *p.skip_flag != 0);
+  const bool skip = skip_word != 0;
   // Dual-issuer mode (one tile per CTA, i.e. the small-M GEMMs of the decoder steps).  Measured: the K loop of a
   // lone CTA costs ~0.3 us per k-block whatever the ring depth or the tile width (scripts/ingest_*_probe.py) -- the
   // time ONE thread needs to issue four tcgen05.mma + a commit -- so K = 3072 is 14 us however few rows there are.
@@ -605,22 +611,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (ptx::elect_one()) ptx::umma_commit(tfull_bar(w));
       __syncwarp();
     }
-  } else if (warp == 0) {
-    // ===================================================================== TMA producer (warp-uniform loop, one
-    // elected lane issues)
+  } else if (warp == 0 || warp == kSecondProducerWarp) {
+    // ===================================================================== TMA producers (warp-uniform loops, one
+    // elected lane issues).  Two warps, even / odd k-blocks: with no loads and no MMAs at all the ring handshake
+    // alone cost 0.07 us per k-block (try_wait -> elect -> expect_tx -> issue -> syncwarp is one dependent chain
+    // of shared-memory sync ops), and the loads doubled it (scripts/launch_floor_probe.py).  The first kStages
+    // k-blocks find the ring empty and skip the wait.
     {
-      int stage = 0; uint32_t phase = 0;
+      const int w = (warp == 0) ? 0 : 1;
+      int g = 0;                                  // running k-block index of this CTA over all its tiles
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          if (!bounded_wait(empty_bar(stage), phase ^ 1u, 1)) goto done;
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          if ((g & 1) != w) continue;
+          const int stage = g % Cfg::kStages;
+          if (g >= Cfg::kStages) {
+            const uint32_t phase = (uint32_t)((g / Cfg::kStages) & 1);
+            if (!bounded_wait(empty_bar(stage), phase ^ 1u, 1)) goto done;
+          }
           if (ptx::elect_one()) {
             ptx::mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
             ptx::tma_load_2d(smem_a0 + stage * Cfg::kABytes, &tmap_a, kb * kBK, m_blk * kBM, full_bar(stage));
             ptx::tma_load_2d(smem_b0 + stage * Cfg::kBBytes, &tmap_w, kb * kBK, n_blk * BN, full_bar(stage));
           }
           __syncwarp();
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -661,7 +675,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
-  } else if (warp >= kFirstEpiWarp) {
+  } else if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + kEpiWarps) {
     // ===================================================================== epilogue warps
     const int e = warp - kFirstEpiWarp;
     const int quad = warp & 3;                // TMEM lane quadrant this warp may access
@@ -670,6 +684,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int acc = 0; uint32_t acc_phase = 0;
     int cur_len = 0;
     if (EPI == EPI_ARGMAX) cur_len = (p.cur_len != nullptr) ? *p.cur_len : (1 << 30);
+    // Pull this warp's bias segment into L1 while the K loop runs.  In the decoder steps the parameters are
+    // HBM-cold every time (weights and cross K/V stream through L2 between two uses), and the epilogue's bias load
+    // sat behind the accumulator wait: one DRAM latency on the critical path of every small GEMM.
+    if (p.bias != nullptr && (int)blockIdx.x < num_tiles) {
+      const int c = ((int)blockIdx.x % tiles_n) * BN + half * (BN / 2) + lane * 4;
+      if (lane < BN / 8 && c < p.N) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+        asm volatile("" ::"f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w));
+      }
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
       if (!bounded_wait(tfull_bar(acc), acc_phase, 4)) break;

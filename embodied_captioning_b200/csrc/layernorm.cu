@@ -56,12 +56,24 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         long long ldy, int rows, int width,
                                                         const int* __restrict__ skip_flag) {
   pdl_trigger_top();
-  pdl_wait();
-  if (skip_flag != nullptr && *skip_flag != 0) return;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int nvec = width >> 2;
+  // gamma / beta first, and before the dependency wait (they are parameters, not the previous kernel's output): in the
+  // decoder steps they are HBM-cold every time (557 MB of weights + 9.6 GB of cross K/V pass through L2 per step), and
+  // loading them after the row statistics put that miss, plus one L2 round trip per vector, on the critical path
+  // of a 3 us kernel.
+  float4 g[kLnMaxVec], b[kLnMaxVec];
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+      b[i] = __ldg(reinterpret_cast<const float4*>(beta) + c);
+    }
+  }
+  pdl_wait();
+  if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
   float4 v[kLnMaxVec];
 #pragma unroll
@@ -69,12 +81,29 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     const int c = lane + i * 32;
     v[i] = (c < nvec) ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  if (skip_flag != nullptr && *skip_flag != 0) return;      // after the row loads are in flight
   float mean, rstd;
   ln_stats(v, nvec, lane, width, mean, rstd);
   pdl_trigger_bottom();
-  void* yrow = kBf16Out ? (void*)(reinterpret_cast<bf16*>(y) + (size_t)row * ldy)
-                        : (void*)(reinterpret_cast<float*>(y) + (size_t)row * ldy);
-  ln_store<kBf16Out>(v, nvec, lane, mean, rstd, gamma, beta, yrow);
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g[i].x + b[i].x;
+      o.y = (v[i].y - mean) * rstd * g[i].y + b[i].y;
+      o.z = (v[i].z - mean) * rstd * g[i].z + b[i].z;
+      o.w = (v[i].w - mean) * rstd * g[i].w + b[i].w;
+      if (kBf16Out) {
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(y) + (size_t)row * ldy)[c] = pk;
+      } else {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + (size_t)row * ldy)[c] = o;
+      }
+    }
+  }
 }
 
 int layernorm(const float* x, long long ldx, const float* gamma, const float* beta, void* y, long long ldy,
