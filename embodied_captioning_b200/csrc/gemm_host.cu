@@ -159,6 +159,13 @@ static int launch_epi(const GemmArgs& a, cudaStream_t stream) {
   } else {
   static const int forced = [] { const char* e = getenv("EC_GEMM_BN"); return e ? atoi(e) : 0; }();
   if (forced == 256) return launch_tile<256, EPI>(a, stream);
+  if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
+    // 128 x 192 tiles when they turn a ragged second wave of 128 x 128 tiles into one wave (decoder FC1:
+    // 1024 x 3072 is 192 tiles of 128 x 128 on 148 SMs, but 128 tiles of 128 x 192)
+    const int t128 = ceil_div(a.M, kBM) * ceil_div(a.N, 128), t192 = ceil_div(a.M, kBM) * ceil_div(a.N, 192);
+    if (forced == 192 || (forced == 0 && a.N % 192 == 0 && t128 > num_sms() && t192 <= num_sms()))
+      return launch_tile<192, EPI>(a, stream);
+  }
   if (forced == 128) return launch_tile<128, EPI>(a, stream);
   if (forced == 64) return launch_tile<64, EPI>(a, stream);
   const int sms = num_sms();

@@ -185,11 +185,11 @@ constexpr bool kDualIssue = true;
 #endif
 
 template <int BN> struct TileCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (BN >= 192) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = 2 * BN;                   // two accumulator stages
+  static constexpr int kTmemCols = (BN == 192) ? 512 : 2 * BN;   // two accumulator stages (allocations are powers of 2)
   static constexpr int kBarBytes = 1024;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + kBarBytes + 1024 /*align*/;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");

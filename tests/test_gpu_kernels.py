@@ -16,6 +16,8 @@ GEMM_SHAPES = [
     (128, 256, 64), (128, 256, 128), (256, 512, 1024), (257, 384, 128), (1000, 3072, 1024), (4, 768, 768),
     (50, 128, 3072), (1024, 768, 3072), (300, 1536, 768), (130, 64, 64), (513, 1000, 592), (2570, 1024, 4096),
     (3855, 3072, 1024),
+    # one wave of 128 x 192 tiles instead of a ragged second wave of 128 x 128 (bf16 / GELU epilogues); ragged M
+    (1001, 3072, 768), (700, 4608, 512),
     # enough 256 x 256 tiles for the CTA-pair (cta_group::2) kernel; ragged M, N and K tails
     (20000, 1024, 1024), (19001, 1000, 592), (9733, 2304, 768),
 ]
