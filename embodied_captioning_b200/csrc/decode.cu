@@ -144,19 +144,20 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __res
   if (pair >= batch * heads) return;
   const int b = pair / heads, h = pair % heads;
   // the three control words in ONE round trip (as dependent early-outs they were three L2 latencies in a row)
-  const int done = st->done, cur_len = st->cur_len;
-  const unsigned char fin = finished[b];
-  if (done || fin) return;
-  const int pos = cur_len - 1;
   const int C = heads * D;
   const int sub = lane & 7, grp = lane >> 3;
   const bf16* row = qkv + (size_t)b * 3 * C + h * D + sub * 8;
+  const int done = st->done, cur_len = st->cur_len;
+  const unsigned char fin = finished[b];
+  const uint4 knew = *reinterpret_cast<const uint4*>(row + C), vnew = *reinterpret_cast<const uint4*>(row + 2 * C);
+  float qf[8];
+  load_q_slice(row, qf);                      // the new token's q, k, v ride in the same round trip
+  if (done || fin) return;
+  const int pos = cur_len - 1;
   bf16* kc = kcache + ((size_t)b * max_len) * C + h * D + sub * 8;
   bf16* vc = vcache + ((size_t)b * max_len) * C + h * D + sub * 8;
-  if (grp == 0) *reinterpret_cast<uint4*>(kc + (size_t)pos * C) = *reinterpret_cast<const uint4*>(row + C);
-  if (grp == 1) *reinterpret_cast<uint4*>(vc + (size_t)pos * C) = *reinterpret_cast<const uint4*>(row + 2 * C);
-  float qf[8];
-  load_q_slice(row, qf);
+  if (grp == 0) *reinterpret_cast<uint4*>(kc + (size_t)pos * C) = knew;
+  if (grp == 1) *reinterpret_cast<uint4*>(vc + (size_t)pos * C) = vnew;
   __syncwarp();     // the appended row is read back by other lanes of this warp below
   float acc[8], inv;
   warp_attend(qf, kc, vc, (size_t)C, pos + 1, lane, acc, inv);

@@ -49,12 +49,42 @@ __device__ __forceinline__ void ln_store(const float4 (&v)[kLnMaxVec], int nvec,
   }
 }
 
+// Throughput variant (image tower: 263 k rows per launch, HBM-bound): few registers, four blocks per SM.
 template <bool kBf16Out>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long ldx,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, void* __restrict__ y,
                                                         long long ldy, int rows, int width,
                                                         const int* __restrict__ skip_flag) {
+  pdl_trigger_top();
+  pdl_wait();
+  if (skip_flag != nullptr && *skip_flag != 0) return;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = width >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
+  float4 v[kLnMaxVec];
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = lane + i * 32;
+    v[i] = (c < nvec) ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float mean, rstd;
+  ln_stats(v, nvec, lane, width, mean, rstd);
+  pdl_trigger_bottom();
+  void* yrow = kBf16Out ? (void*)(reinterpret_cast<bf16*>(y) + (size_t)row * ldy)
+                        : (void*)(reinterpret_cast<float*>(y) + (size_t)row * ldy);
+  ln_store<kBf16Out>(v, nvec, lane, mean, rstd, gamma, beta, yrow);
+}
+
+// Latency variant (decoder steps: ~1 k rows, a 2.5 us kernel on the critical path of the step).
+template <bool kBf16Out>
+__global__ void __launch_bounds__(256) layernorm_small_kernel(const float* __restrict__ x, long long ldx,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, void* __restrict__ y,
+                                                              long long ldy, int rows, int width,
+                                                              const int* __restrict__ skip_flag) {
   pdl_trigger_top();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -115,12 +145,13 @@ int layernorm(const float* x, long long ldx, const float* gamma, const float* be
   const int wpb = 8;
   const int grid = ceil_div(rows, wpb);
   note_launches(1);
+  const bool small = rows <= 8192;      // one wave of blocks: latency, not bandwidth, is what counts
   if (y_is_bf16)
-    EC_CHECK_CUDA(launch_kernel(layernorm_kernel<true>, dim3(grid), dim3(wpb * 32), 0, stream, x, ldx, gamma, beta, y, ldy,
-                                rows, width, skip_flag));
+    EC_CHECK_CUDA(launch_kernel(small ? layernorm_small_kernel<true> : layernorm_kernel<true>, dim3(grid), dim3(wpb * 32), 0,
+                                stream, x, ldx, gamma, beta, y, ldy, rows, width, skip_flag));
   else
-    EC_CHECK_CUDA(launch_kernel(layernorm_kernel<false>, dim3(grid), dim3(wpb * 32), 0, stream, x, ldx, gamma, beta, y,
-                                ldy, rows, width, skip_flag));
+    EC_CHECK_CUDA(launch_kernel(small ? layernorm_small_kernel<false> : layernorm_kernel<false>, dim3(grid), dim3(wpb * 32),
+                                0, stream, x, ldx, gamma, beta, y, ldy, rows, width, skip_flag));
   return EC_OK;
 }
 
