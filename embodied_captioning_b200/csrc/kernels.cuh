@@ -10,6 +10,13 @@ namespace ec {
 int layernorm(const float* x, long long ldx, const float* gamma, const float* beta, void* y, long long ldy,
               bool y_is_bf16, int rows, int width, const int* skip_flag, cudaStream_t stream);
 
+// Fold a LayerNorm's affine part into the nn.Linear that follows it:  LN(x) @ W^T + b = xhat @ (W * gamma)^T + (b + W @ beta)
+// with xhat = (x - mean) * rstd.  W [n_out, k] bf16, gamma / beta [k], bias [n_out] -> w_fold bf16 [n_out, k], b_fold [n_out].
+int fold_layernorm_into_linear(const bf16* w, const float* bias, const float* gamma, const float* beta, bf16* w_fold,
+                               float* b_fold, int n_out, int k, cudaStream_t stream);
+// out[i] = value
+int fill_f32(float* out, int n, float value, cudaStream_t stream);
+
 // Vision stem: x[b,0,:] = cls + pos[0]; x[b,1+p,:] = patch[b,p,:] + pos[1+p]; then ln_pre -> fp32 [B*tokens, W].
 int vision_embed_ln_pre(const float* patch_emb, const float* cls, const float* pos, const float* gamma,
                         const float* beta, float* out, int batch, int tokens, int width, cudaStream_t stream);

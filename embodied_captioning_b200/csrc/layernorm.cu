@@ -156,6 +156,45 @@ int layernorm(const float* x, long long ldx, const float* gamma, const float* be
 }
 
 // ---------------------------------------------------------------------------------------------------
+// One warp per output row of the folded linear (model-load time, not on the hot path).
+__global__ void __launch_bounds__(256) fold_ln_linear_kernel(const bf16* __restrict__ w, const float* __restrict__ bias,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, bf16* __restrict__ w_fold,
+                                                             float* __restrict__ b_fold, int n_out, int k) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_out) return;
+  float acc = 0.f;
+  for (int c = lane; c < k; c += 32) {
+    const float wv = __bfloat162float(w[(size_t)row * k + c]);
+    acc += wv * beta[c];
+    w_fold[(size_t)row * k + c] = __float2bfloat16_rn(wv * gamma[c]);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) b_fold[row] = (bias != nullptr ? bias[row] : 0.f) + acc;
+}
+
+int fold_layernorm_into_linear(const bf16* w, const float* bias, const float* gamma, const float* beta, bf16* w_fold,
+                               float* b_fold, int n_out, int k, cudaStream_t stream) {
+  if (n_out <= 0) return EC_OK;
+  fold_ln_linear_kernel<<<ceil_div(n_out, 8), 256, 0, stream>>>(w, bias, gamma, beta, w_fold, b_fold, n_out, k);
+  EC_POST_LAUNCH();
+  return EC_OK;
+}
+
+__global__ void fill_f32_kernel(float* out, int n, float value) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = value;
+}
+
+int fill_f32(float* out, int n, float value, cudaStream_t stream) {
+  if (n <= 0) return EC_OK;
+  fill_f32_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(out, n, value);
+  EC_POST_LAUNCH();
+  return EC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) vision_embed_ln_pre_kernel(const float* __restrict__ patch_emb,
                                                                   const float* __restrict__ cls,
                                                                   const float* __restrict__ pos,

@@ -72,6 +72,8 @@ Model::Model(const ec_config& c, int dev) : cfg(c), device(dev) {
   // Encoder 180 -> 220 ms, decoder 113 -> 150 ms at 1024 crops.  Opt-in only (EC_FUSE_LN=1).
   static const int env_pf = [] { const char* e = getenv("EC_PREFETCH_WEIGHTS"); return e ? atoi(e) : 1; }();
   prefetch_weights = env_pf != 0;
+  static const int env_lnkv = [] { const char* e = getenv("EC_SHARED_LNKV"); return e ? atoi(e) : 1; }();
+  shared_lnkv = env_lnkv != 0;
   static const int env_fuse = [] { const char* e = getenv("EC_FUSE_LN"); return e ? atoi(e) : 0; }();
   if (env_fuse == 0) fuse_ln = false;
   // image tower: the CTA-local tail (no atomics, contiguous tile schedule) also loses -- the epilogue warps that run it
@@ -232,6 +234,29 @@ int Model::finalize(cudaStream_t stream) {
     g.A = lnq; g.lda = E; g.W = w_pool_q; g.ldw = E; g.M = Q; g.N = E; g.K = E; g.bias = b_pool_qkv;
     g.out = pool_q_proj; g.ldo = E;
     rc = gemm_bf16(g, EPI_BF16, stream);
+  }
+  // pre-multiplied cross K/V projections (rows [T, 3T) of in_proj) for the shared normalisation of the image tokens
+  if (rc == EC_OK && shared_lnkv && !dcross.empty()) {
+    const int T = cfg.text_width;
+    if (unit_gamma == nullptr) {
+      if (cudaMalloc(&unit_gamma, 2 * (size_t)T * sizeof(float)) != cudaSuccess) rc = EC_ERR_CUDA;
+      else { owned.push_back(unit_gamma); zero_beta = unit_gamma + T; }
+    }
+    if (rc == EC_OK) rc = fill_f32(unit_gamma, T, 1.0f, stream);
+    if (rc == EC_OK) rc = fill_f32(zero_beta, T, 0.0f, stream);
+    wkv_fold.resize(dcross.size(), nullptr);
+    bkv_fold.resize(dcross.size(), nullptr);
+    for (size_t l = 0; l < dcross.size() && rc == EC_OK; ++l) {
+      if (wkv_fold[l] == nullptr) {
+        if (cudaMalloc(&wkv_fold[l], 2 * (size_t)T * T * sizeof(bf16)) != cudaSuccess ||
+            cudaMalloc(&bkv_fold[l], 2 * (size_t)T * sizeof(float)) != cudaSuccess) { rc = EC_ERR_CUDA; break; }
+        owned.push_back(wkv_fold[l]);
+        owned.push_back(bkv_fold[l]);
+      }
+      const Block& b = dcross[l];
+      rc = fold_layernorm_into_linear(b.w_qkv + (size_t)T * T, b.b_qkv + T, b.lnkv_g, b.lnkv_b, wkv_fold[l], bkv_fold[l],
+                                      2 * T, T, stream);
+    }
   }
   cudaError_t e = cudaStreamSynchronize(stream);
   cudaFree(lnq);
@@ -568,6 +593,14 @@ int Model::decode_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int
 int Model::prefill_cross_kv(const DecodeWs& w, const float* embs, int n, cudaStream_t s) {
   const int T = cfg.text_width, NK = cfg.n_queries - 1;
   const int rows = n * NK;
+  if (shared_lnkv && (int)wkv_fold.size() == cfg.mm_layers) {
+    // one normalisation of the image tokens for all layers; gamma / beta sit in the pre-multiplied weights (finalize)
+    EC_TRY(layernorm(embs, T, unit_gamma, zero_beta, w.ln_kv, T, true, rows, T, nullptr, s));
+    for (int l = 0; l < cfg.mm_layers; ++l)
+      EC_TRY(linear(w.ln_kv, T, wkv_fold[l], T, bkv_fold[l], rows, 2 * T, T, w.cross_kv + (size_t)l * rows * 2 * T,
+                    2 * T, EPI_BF16, nullptr, 0, nullptr, s));
+    return EC_OK;
+  }
   for (int l = 0; l < cfg.mm_layers; ++l) {
     const Block& b = dcross[l];
     EC_TRY(layernorm(embs, T, b.lnkv_g, b.lnkv_b, w.ln_kv, T, true, rows, T, nullptr, s));

@@ -31,6 +31,12 @@ struct Model {
   bool fuse_ln = true;             // (ctor: off unless EC_FUSE_LN=1) LayerNorms computed by the residual GEMM's fused tail
   bool fuse_ln_encoder = false;    // image tower: LayerNorm tails inside the CTA-pair residual GEMMs (EC_FUSE_LN_ENC=1: on; measured slower)
   bool prefetch_weights = true;    // decoder GEMMs prefetch the next GEMM's weights into L2 (EC_PREFETCH_WEIGHTS=0: off)
+  // cross-K/V prefill: the 12 ln_1_kv LayerNorms of the image tokens differ only in gamma / beta, so the tokens are
+  // normalised ONCE and the affine parts live in pre-multiplied K/V projection weights (EC_SHARED_LNKV=0: off)
+  bool shared_lnkv = true;
+  std::vector<bf16*> wkv_fold;
+  std::vector<float*> bkv_fold;
+  float *unit_gamma = nullptr, *zero_beta = nullptr;
   int* ln_counters = nullptr;      // row-block arrival counters of the fused tails (zero between launches)
   bool use_tc_attention = false;   // tcgen05/TMEM attention for the ViT blocks (option "tc_attention")
   int patch_k = 0, patch_ld = 0;
