@@ -296,6 +296,8 @@ def main():
 
     # ---- per-stage breakdown (one extra untimed-for-value step) for the decoder HBM line
     def timed(fn):
+        # second of two calls: the first one may (re)capture the decoder's step graph for this argument set
+        fn(); torch.cuda.synchronize(dev)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); r = fn(); b.record(); torch.cuda.synchronize(dev)
         return r, a.elapsed_time(b)
