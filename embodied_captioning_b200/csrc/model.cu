@@ -685,7 +685,12 @@ int Model::decode_greedy(const float* embs, int n, int seq_len, int min_len, int
   const DecodeWs w = carve_decode(*this, ws, n, seq_len);
   EC_REQUIRE(ws_bytes >= w.bytes, EC_ERR_WORKSPACE, "decode workspace %zu < %zu", ws_bytes, w.bytes);
   EC_TRY(prefill_cross_kv(w, embs, n, s));
-  return run_steps(w, tokens, seq_len, n, seq_len, min_len, logits, false, seq_len - 1, s);
+  // Decode into the workspace's own token table and copy out at the end: the caller's output buffer is usually a
+  // fresh allocation, and its address is part of the step graph's key -- a new address would re-capture and
+  // re-instantiate the 258-node graph on every call.
+  EC_TRY(run_steps(w, w.tokens_tf, seq_len, n, seq_len, min_len, logits, false, seq_len - 1, s));
+  EC_CHECK_CUDA(cudaMemcpyAsync(tokens, w.tokens_tf, (size_t)n * seq_len * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  return EC_OK;
 }
 
 int Model::forward_logits(const float* embs, const int* text, int n, int t, float* logits, void* ws, size_t ws_bytes,
