@@ -4,12 +4,14 @@
 //   gemm_tcgen05_pair_kernel  CTA pairs (cluster of 2), tcgen05.mma.cta_group::2, UMMA 256 x 256 x 16: the large GEMMs
 //   gemm_tcgen05_kernel       one CTA per tile, cta_group::1, UMMA 128 x BN x 16: small-M GEMMs (decoder steps, pooler)
 // Warp roles in both:
-//   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx)
+//   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx); in the 1-CTA kernel it
+//                 also initialises the barriers and issues the first ring of loads before the CTA-wide sync
 //   warp 1      : MMA issuer     (warp-uniform loop, one elected lane issues tcgen05.mma / tcgen05.commit)
-//   warp 2      : TMEM allocator
-//   warp 3      : L2 prefetch of the next GEMM's weights (decoder steps), otherwise idle
+//   warp 2      : TMEM allocator; then L2 prefetch of the next GEMM's weights (decoder steps)
+//   warp 3      : 1-CTA kernel, single-tile launches: second MMA issuer (odd k-blocks, second TMEM stage); else idle
 //   warps 4..   : 8 or 16 epilogue warps (tcgen05.ld 32x32b -> bias / GELU / residual / arg-max in registers ->
 //                 per-warp swizzled shared-memory transpose -> coalesced global row segments)
+//   warp 12     : 1-CTA kernel only: second TMA producer (odd k-blocks)
 // Persistent CTAs (1 per SM) walk the tile list; two TMEM accumulator stages overlap epilogue(i) with mainloop(i+1).
 #pragma once
 #include "gemm_sm100.cuh"
@@ -242,7 +244,7 @@ struct EpiParams {
   // fused LayerNorm tail (EPI_F32_RESID only, ln_out != nullptr): see ln_tail()
   const float* ln_g; const float* ln_b; bf16* ln_out; int ld_ln; int* ln_cnt; int ln_tiles_n;
   // L2 prefetch of the NEXT GEMM's weights (decoder steps: weights cycle through L2 once per step, so every K panel
-  // would otherwise arrive at HBM latency); issued by the otherwise idle warp 3
+  // would otherwise arrive at HBM latency); issued by warp 2 once it has allocated the tensor memory
   const unsigned char* pf_ptr; unsigned long long pf_bytes;
 };
 
