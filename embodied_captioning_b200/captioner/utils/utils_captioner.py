@@ -1,12 +1,21 @@
-"""`select_captioner(cfg)` (experimenting_env/captioner/utils/utils_captioner.py:4-11)."""
+"""Captioner factory: `select_captioner(cfg)` with the behaviour of
+experimenting_env/captioner/utils/utils_captioner.py:4-11 (case-insensitive `cfg.arch_name`, an AssertionError with
+the reference's message for anything but "coca" / "blip2")."""
 from ..models.coca.coca import CoCa
+
+_SUPPORTED = ("coca", "blip2")
+
+
+def _blip2_not_here(cfg):
+    # BLIP-2 (OPT-2.7B int8 through bitsandbytes) is a second captioner family outside the B200 hot path
+    #  and is not re-implemented; failing loudly beats returning a silent stand-in.
+    raise NotImplementedError("arch_name='blip2' is outside the B200-native hot path; use the reference's BLIP2 wrapper")
+
+
+_BUILDERS = {"coca": CoCa, "blip2": _blip2_not_here}
 
 
 def select_captioner(cfg):
-    arch_name = cfg.arch_name
-    assert arch_name.lower() in ["coca", "blip2"], "Currently, only 'coca' and 'blip2' architectures are supported."
-    if arch_name.lower() == "coca":
-        return CoCa(cfg)
-    # BLIP-2 (OPT-2.7B int8 through bitsandbytes) is a second captioner family outside the B200 hot path
-    # (SURVEY.md C8): it is not re-implemented here.
-    raise NotImplementedError("arch_name='blip2' is outside the B200-native hot path; use the reference's BLIP2 wrapper")
+    key = str(cfg.arch_name).lower()
+    assert key in _SUPPORTED, "Currently, only 'coca' and 'blip2' architectures are supported."
+    return _BUILDERS[key](cfg)
