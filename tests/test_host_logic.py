@@ -81,3 +81,21 @@ def test_select_captioner_rejects_unknown_arch():
     cfg = Configuration(arch_name="florence", model_name="x", checkpoint_name=None, height=224, width=224)
     with pytest.raises(AssertionError):
         select_captioner(cfg.captioner)
+
+
+def test_configuration_holder_matches_reference_signature():
+    """experimenting_env/captioner/utils/utils.py:2-12: five optional fields, positional or keyword, held under
+    `.captioner`; BLIP-2 is named by the factory but not built here."""
+    from embodied_captioning_b200.captioner.utils.utils import CaptionerField, Configuration
+    from embodied_captioning_b200.captioner.utils.utils_captioner import select_captioner
+    a = Configuration("coca", "coca_ViT-L-14", "ckpt.pt", 224, 224)
+    b = Configuration(arch_name="coca", model_name="coca_ViT-L-14", checkpoint_name="ckpt.pt", height=224, width=224)
+    assert a.captioner == b.captioner == CaptionerField("coca", "coca_ViT-L-14", "ckpt.pt", 224, 224)
+    empty = Configuration()
+    assert (empty.captioner.arch_name, empty.captioner.width) == (None, None)
+    with pytest.raises(TypeError):
+        Configuration(arch="coca")
+    with pytest.raises(TypeError):
+        Configuration("coca", arch_name="coca")
+    with pytest.raises(NotImplementedError):
+        select_captioner(Configuration(arch_name="BLIP2").captioner)
