@@ -130,6 +130,18 @@ def current_stream(device=None) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def cuda_device(device=None):
+    """Normalise `device` to an indexed CUDA device: an index-less 'cuda' means the CURRENT device (what every torch
+    allocation resolves it to), never device 0 -- the native handle and torch's buffers must agree under torchrun."""
+    import torch
+    d = torch.device("cuda" if device is None else device)
+    if d.type != "cuda":
+        raise NativeError(f"device {d} is not a CUDA device; there is no CPU execution path")
+    if d.index is not None:
+        return d
+    return torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+
+
 def require_cuda():
     import torch
     if not torch.cuda.is_available():

@@ -27,6 +27,17 @@ from ....synth import state_dict_spec
 GENERATION_TYPES = {"top_k": "top_k", "top_p": None, "beam_search": None}
 
 
+def strip_checkpoint_prefixes(state_dict):
+    """Keys as the reference's checkpoints carry them: `module.` from DDP (evaluate_finetuned_model.py:141-146) and
+    `model.` from the `CoCa` wrapper whose state dict `Captioner` saves and loads (predictor_utils.py:182-185); the
+    wrapper prefix is only dropped when every tensor key carries it (no open_clip CoCa tensor starts with `model.`)."""
+    sd = {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+    if sd and all(k.startswith("model.") for k in sd):
+        sd = {k[6:]: v for k, v in sd.items()}
+        sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+    return sd
+
+
 class _Visual:
     """Stand-in for `model.visual`: callers only read `.preprocess_cfg` / `.image_size` (factory.py:418)."""
 
@@ -45,7 +56,7 @@ class CoCa(nn.Module):
         self.pad_id = cfg.pad_token_id if pad_id == 0 else pad_id
         self.context_length = cfg.context_length
         self.visual = _Visual(cfg)
-        self._device = torch.device(device)
+        self._device = nat.cuda_device(device)     # always indexed: 'cuda' = the current device, not device 0
         self.output_device: Optional[torch.device] = None     # set by .to('cpu') for callers that asked for CPU
         self._handle = C.c_void_p()
         self._loaded = False
@@ -110,7 +121,7 @@ class CoCa(nn.Module):
         ec = nat.EcConfig(c.embed_dim, c.image_size, c.patch_size, c.vision_width, c.vision_layers, c.vision_head_dim,
                           c.pooler_heads, c.n_queries, c.text_width, c.text_heads, c.text_layers, c.mm_layers,
                           c.mm_heads, c.context_length, c.vocab_size, c.sot_token_id, c.eos_token_id, c.pad_token_id)
-        nat.check(nat.lib().ec_model_create(C.byref(ec), self._device.index or 0, C.byref(self._handle)),
+        nat.check(nat.lib().ec_model_create(C.byref(ec), self._device.index, C.byref(self._handle)),
                   "ec_model_create")
         nat.check(nat.lib().ec_model_set_option(self._handle, b"decode_graph", int(self._graph)), "ec_model_set_option")
         nat.check(nat.lib().ec_model_set_option(self._handle, b"tc_attention", int(self._tc_attention)))
@@ -136,7 +147,7 @@ class CoCa(nn.Module):
     def load_state_dict(self, state_dict, strict: bool = True):
         """open_clip-layout tensors (names/shapes: SURVEY.md Appendix A); `module.` prefixes are stripped like
         scripts/evaluate_finetuned_model.py:141-146 does."""
-        sd = {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+        sd = strip_checkpoint_prefixes(state_dict)
         spec = state_dict_spec(self.cfg)
         missing = [k for k in spec if k not in sd]
         unexpected = [k for k in sd if k not in spec]
@@ -240,6 +251,11 @@ class CoCa(nn.Module):
         c = self.cfg
         embs = embs.contiguous()
         N, t = text.shape
+        if N * t > 0:
+            lo, hi = int(text.min().item()), int(text.max().item())
+            if lo < 0 or hi >= c.vocab_size:      # the embedding gather has no bounds check on the device
+                raise nat.NativeError(f"ec_forward_logits failed: EC_ERR_INVALID: token ids must lie in [0, "
+                                      f"{c.vocab_size}), got [{lo}, {hi}] (ignore_index / foreign-tokenizer ids?)")
         tx = text.to(torch.int32).contiguous()
         out = torch.empty((t, N, c.vocab_size), device=self._device, dtype=torch.float32)
         lib = nat.lib()

@@ -52,15 +52,23 @@ class SimpleTokenizer:
         path = _find_vocab(bpe_path)
         self.has_vocab = path is not None
         self.decoder = {}
+        self._cache = {SOT_TEXT: [SOT_TEXT], EOT_TEXT: [EOT_TEXT]}
+        self._pat = None
         if self.has_vocab:
             merges = gzip.open(path).read().decode("utf-8").split("\n")
-            merges = merges[1:vocab_size - 256 - 2 + 1]
-            merges = [tuple(m.split()) for m in merges]
+            # upstream keeps `49152 - 256 - 2 + 1` lines = 48 894 merges after the header: 512 byte symbols +
+            # merges + 2 specials = 49 408, so <start_of_text> / <end_of_text> are the last two ids
+            merges = merges[1:vocab_size - 512 - 2 + 1]
+            merges = [tuple(m.split()) for m in merges if m.strip()]
             vocab = list(self.byte_encoder.values())
             vocab = vocab + [v + "</w>" for v in vocab]
             vocab.extend("".join(m) for m in merges)
             vocab.extend([SOT_TEXT, EOT_TEXT])
+            if len(vocab) != vocab_size:
+                raise RuntimeError(f"BPE table {path} yields {len(vocab)} entries, the model has {vocab_size} "
+                                   "(merge file too short for this vocabulary)")
             self.encoder = dict(zip(vocab, range(len(vocab))))
+            assert self.encoder[SOT_TEXT] == self.sot_token_id and self.encoder[EOT_TEXT] == self.eot_token_id
             self.decoder = {v: k for k, v in self.encoder.items()}
             self.bpe_ranks = dict(zip(merges, range(len(merges))))
 
@@ -79,8 +87,66 @@ class SimpleTokenizer:
         text = "".join(self.decoder[t] for t in toks)
         return bytearray([self.byte_decoder[c] for c in text]).decode("utf-8", errors="replace").replace("</w>", " ")
 
+    # ------------------------------------------------------------------ encode side (CLIP byte-level BPE)
+    def _merge_word(self, word: str) -> List[str]:
+        """Greedy lowest-rank-first pair merging of one pre-token; the last symbol carries the `</w>` marker."""
+        cached = self._cache.get(word)
+        if cached is not None:
+            return cached
+        syms = list(word[:-1]) + [word[-1] + "</w>"]
+        while len(syms) > 1:
+            best_rank, best_at = None, -1
+            for i in range(len(syms) - 1):
+                r = self.bpe_ranks.get((syms[i], syms[i + 1]))
+                if r is not None and (best_rank is None or r < best_rank):
+                    best_rank, best_at = r, i
+            if best_rank is None:
+                break
+            a, b = syms[best_at], syms[best_at + 1]
+            out, i = [], 0
+            while i < len(syms):                       # merge EVERY occurrence of the winning pair, left to right
+                if i + 1 < len(syms) and syms[i] == a and syms[i + 1] == b:
+                    out.append(a + b); i += 2
+                else:
+                    out.append(syms[i]); i += 1
+            syms = out
+        self._cache[word] = syms
+        return syms
+
+    def encode(self, text: str) -> List[int]:
+        if not self.has_vocab:
+            raise RuntimeError("encode() needs the BPE merge table (EC_BPE_VOCAB / bpe_path=)")
+        import html
+        import regex
+        if self._pat is None:
+            self._pat = regex.compile(r"<start_of_text>|<end_of_text>|'s|'t|'re|'ve|'m|'ll|'d|[\p{L}]+|[\p{N}]|"
+                                      r"[^\s\p{L}\p{N}]+", regex.IGNORECASE)
+        text = html.unescape(html.unescape(text))
+        text = " ".join(text.split()).strip().lower()
+        ids: List[int] = []
+        for piece in self._pat.findall(text):
+            if piece in (SOT_TEXT, EOT_TEXT):
+                ids.append(self.encoder[piece])
+                continue
+            mapped = "".join(self.byte_encoder[b] for b in piece.encode("utf-8"))
+            ids.extend(self.encoder[sym] for sym in self._merge_word(mapped))
+        return ids
+
     def __call__(self, texts, context_length: Optional[int] = None):
-        raise NotImplementedError("text encoding is not on the captioning hot path (generate() starts from SOT)")
+        """`open_clip.tokenize`: int64 [N, context_length] = SOT + ids + EOT, zero padded; over-long rows are cut and
+        end with EOT."""
+        import torch
+        if isinstance(texts, str):
+            texts = [texts]
+        L = context_length or self.context_length
+        out = torch.zeros(len(texts), L, dtype=torch.long)
+        for i, t in enumerate(texts):
+            ids = [self.sot_token_id] + self.encode(t) + [self.eot_token_id]
+            if len(ids) > L:
+                ids = ids[:L]
+                ids[-1] = self.eot_token_id
+            out[i, :len(ids)] = torch.tensor(ids)
+        return out
 
 
 _default: Optional[SimpleTokenizer] = None

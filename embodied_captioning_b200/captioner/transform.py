@@ -13,6 +13,7 @@ from typing import Optional, Sequence
 import numpy as np
 import torch
 
+from .. import _native as nat
 from .. import ops
 
 POLICY_AGENT = 0            # goal_exploration.py:95-99, frontier_exploration.py:133-137
@@ -58,11 +59,15 @@ def box_rects(boxes, frame_h: int, frame_w: int, policy: int):
         rects = clamp(rects)
         flags[:] = 1
     elif policy == POLICY_EVAL:
-        bi = np.trunc(b).astype(np.int64)
-        rects[:, 0] = np.where(bi[:, 0] - 10 >= 0, bi[:, 0] - 10, 0)
-        rects[:, 1] = np.where(bi[:, 1] - 10 >= 0, bi[:, 1] - 10, bi[:, 1])
-        rects[:, 2] = np.where(bi[:, 2] + 10 <= frame_w, bi[:, 2] + 10, bi[:, 2])
-        rects[:, 3] = np.where(bi[:, 3] + 10 <= frame_h, bi[:, 3] + 10, bi[:, 3])
+        # The CSV boxes may be floats: the +-10 expansion and the boundary tests run on the raw values (python float
+        # arithmetic), and PIL's `Image.crop` rounds each coordinate half-to-even (`int(round(x))`), not truncates.
+        d = np.asarray(boxes, dtype=np.float64).reshape(-1, 4)
+        e = np.empty_like(d)
+        e[:, 0] = np.where(d[:, 0] - 10 >= 0, d[:, 0] - 10, 0)
+        e[:, 1] = np.where(d[:, 1] - 10 >= 0, d[:, 1] - 10, d[:, 1])
+        e[:, 2] = np.where(d[:, 2] + 10 <= frame_w, d[:, 2] + 10, d[:, 2])
+        e[:, 3] = np.where(d[:, 3] + 10 <= frame_h, d[:, 3] + 10, d[:, 3])
+        rects[:] = np.rint(e).astype(np.int64)                        # np.rint = round-half-even = python round()
     else:
         raise ValueError(f"unknown crop policy {policy}")
     return rects.astype(np.int32), flags
@@ -84,7 +89,7 @@ class ImageTransform:
 
     def __init__(self, size: int = 224, device="cuda:0"):
         self.size = size
-        self.device = torch.device(device)
+        self.device = nat.cuda_device(device)
 
     def _to_u8(self, img) -> np.ndarray:
         if hasattr(img, "convert"):                 # PIL.Image

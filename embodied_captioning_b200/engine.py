@@ -11,6 +11,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
+from . import _native as nat
 from . import ops
 from .captioner.models.coca.factory import create_model
 from .captioner.transform import POLICY_AGENT, box_rects
@@ -19,7 +20,7 @@ from .captioner.transform import POLICY_AGENT, box_rects
 class CaptionEngine:
     def __init__(self, model_name: str = "coca_ViT-L-14", pretrained: Optional[str] = "synthetic",
                  device="cuda:0", decode_graph: bool = True, state_dict=None):
-        self.device = torch.device(device)
+        self.device = nat.cuda_device(device)
         self.model = create_model(model_name, pretrained if state_dict is None else None, device=self.device)
         if state_dict is not None:
             self.model.load_state_dict(state_dict)

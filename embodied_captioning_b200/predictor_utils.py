@@ -20,6 +20,8 @@ class Captioner(nn.Module):
         logger.info("Captioner model loaded successfully")
         if load_checkpoint and checkpoint_path is not None:
             checkpoint = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+            # the reference loads into the WRAPPER (predictor_utils.py:184), so its checkpoints carry `model.`-prefixed
+            # keys; the inner load strips `model.` / `module.` prefixes
             self.model.model.load_state_dict(checkpoint['model'])
             logger.info(f"Captioner model checkpoint loaded successfully from {checkpoint_path}")
         # the reference pins the captioner to the CPU here (predictor_utils.py:187); the B200 build has no

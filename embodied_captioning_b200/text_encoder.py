@@ -78,7 +78,7 @@ class CaptionTextEncoder:
     def __init__(self, cfg: TextEncoderConfig = MINILM_L6, device="cuda:0",
                  tokenizer: Optional[Callable] = None, max_seq_length: int = 256):
         self.cfg = cfg
-        self.device = torch.device(device)
+        self.device = nat.cuda_device(device)
         self.tokenizer = tokenizer
         self.max_seq_length = min(max_seq_length, cfg.max_positions)
         self._handle = C.c_void_p()
@@ -102,7 +102,7 @@ class CaptionTextEncoder:
         if not self._handle:
             ec = nat.EcTextEncConfig(c.vocab_size, c.hidden, c.layers, c.heads, c.intermediate, c.max_positions,
                                      c.type_vocab, c.layer_norm_eps)
-            nat.check(lib.ec_textenc_create(C.byref(ec), self.device.index or 0, C.byref(self._handle)), "ec_textenc_create")
+            nat.check(lib.ec_textenc_create(C.byref(ec), self.device.index, C.byref(self._handle)), "ec_textenc_create")
         strip = lambda k: k[5:] if k.startswith("bert.") else (k[13:] if k.startswith("0.auto_model.") else k)
         sd = {strip(k): v for k, v in state_dict.items()}
         spec = state_dict_spec(c)

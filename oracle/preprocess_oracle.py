@@ -40,7 +40,8 @@ def crop_rect(policy: int, box, frame_h: int, frame_w: int):
     False means numpy slicing semantics (the rectangle is clamped to the frame).
     """
     f32 = np.float32
-    x1, y1, x2, y2 = (f32(v) for v in box)
+    if policy != POLICY_EVAL:
+        x1, y1, x2, y2 = (f32(v) for v in box)
     if policy == POLICY_AGENT:
         r = [int(x1), int(y1), int(x2), int(y2)]          # int() truncation, then rgb[y1:y2, x1:x2]
         return _clamp(r, frame_h, frame_w), False, False
@@ -63,12 +64,14 @@ def crop_rect(policy: int, box, frame_h: int, frame_w: int):
             return r, True, True                           # PIL crop of the BGR->RGB frame
         return _clamp(r, frame_h, frame_w), False, True    # numpy slice, then BGR->RGB
     if policy == POLICY_EVAL:
-        b = [int(v) for v in box]
-        r = [b[0] - 10 if (b[0] - 10) >= 0 else 0,
+        # evaluate_finetuned_model.py:33-37 on the raw (possibly float) CSV values, then `Image.crop`, which rounds
+        # each coordinate with `int(round(x))` (Pillow Image.crop: `map(int, map(round, box))`, half-to-even)
+        b = [float(v) if not isinstance(v, (int, np.integer)) else int(v) for v in box]
+        e = [b[0] - 10 if (b[0] - 10) >= 0 else 0,
              b[1] - 10 if (b[1] - 10) >= 0 else b[1],
              b[2] + 10 if (b[2] + 10) <= frame_w else b[2],
              b[3] + 10 if (b[3] + 10) <= frame_h else b[3]]
-        return r, True, False
+        return [int(round(v)) for v in e], True, False
     raise ValueError(f"unknown crop policy {policy}")
 
 

@@ -99,3 +99,98 @@ def test_configuration_holder_matches_reference_signature():
         Configuration("coca", arch_name="coca")
     with pytest.raises(NotImplementedError):
         select_captioner(Configuration(arch_name="BLIP2").captioner)
+
+
+# ------------------------------------------------------------------------------------------------ BPE tokenizer
+def _write_merge_table(path, merges):
+    import gzip
+    with gzip.open(path, "wt", encoding="utf-8") as f:
+        f.write("#version: 0.2 - synthetic table for tests\n")
+        for a, b in merges:
+            f.write(f"{a} {b}\n")
+        f.write("extra ignored\nlines past\nthe slice\n")     # upstream slices the file; trailing lines are dropped
+
+
+def test_tokenizer_bpe_merge_table_ids_and_roundtrip(tmp_path):
+    """open_clip SimpleTokenizer layout (coca.py:30 consumes its `decode`): 256 byte symbols + 256 `</w>` variants +
+    merges + <start_of_text>/<end_of_text> as the LAST two ids (the merge slice was 256 entries too long)."""
+    merges = [("c", "a"), ("ca", "t</w>"), ("d", "o"), ("do", "g</w>"), ("t", "h"), ("th", "e</w>"), ("o", "n</w>"),
+              ("Ã", "©</w>")]      # last one: the two byte symbols of U+00E9 (C3 A9) as the byte encoder renders them
+    vocab_size = 512 + len(merges) + 2
+    p = tmp_path / "bpe.txt.gz"
+    _write_merge_table(p, merges)
+    tok = SimpleTokenizer(bpe_path=str(p), vocab_size=vocab_size)
+    assert tok.has_vocab and len(tok.encoder) == vocab_size
+    assert tok.encoder["<start_of_text>"] == vocab_size - 2 == tok.sot_token_id
+    assert tok.encoder["<end_of_text>"] == vocab_size - 1 == tok.eot_token_id
+    assert tok.encoder["cat</w>"] == 512 + 1 and tok.encoder["the</w>"] == 512 + 5
+    ids = tok.encode("The cat on the dog")
+    assert ids == [tok.encoder[w] for w in ("the</w>", "cat</w>", "on</w>", "the</w>", "dog</w>")]
+    # unmerged symbols fall back to byte symbols; multi-byte UTF-8 survives the byte decoder
+    ids2 = tok.encode("café cats")
+    assert tok.decode(ids2) == "café cats "
+    assert tok.encoder["Ã©</w>"] in ids2
+    # the string protocol of coca.py:30 on a generated row: SOT, words, EOT, pad ("!" is id 0)
+    row = [tok.sot_token_id] + ids + [tok.eot_token_id, 0, 0]
+    text = tok.decode(row).split("<end_of_text>")[0].replace("<start_of_text>", "")
+    assert text == "the cat on the dog "
+    batch = tok(["the cat", "dog " * 40], context_length=12)
+    assert batch.shape == (2, 12) and batch[0, 0] == tok.sot_token_id and batch[0, 3] == tok.eot_token_id
+    assert batch[0, 4:].eq(0).all() and batch[1, -1] == tok.eot_token_id
+
+
+def test_tokenizer_rejects_short_merge_table(tmp_path):
+    p = tmp_path / "bpe.txt.gz"
+    _write_merge_table(p, [("a", "b</w>")])
+    with pytest.raises(RuntimeError):
+        SimpleTokenizer(bpe_path=str(p), vocab_size=49408)
+
+
+def test_real_vocab_size_slice_matches_upstream_constant():
+    # 49408 = 512 + (49152 - 256 - 2) + 2: upstream keeps lines [1 : 49152-256-2+1] of the merge file
+    assert 49408 - 512 - 2 + 1 == 49152 - 256 - 2 + 1
+
+
+def test_checkpoint_prefixes_are_stripped_like_the_reference_loaders():
+    """predictor_utils.py:182-185 loads `checkpoint['model']` into the WRAPPER (keys `model.visual...`);
+    evaluate_finetuned_model.py:141-146 strips `module.`."""
+    from embodied_captioning_b200.captioner.models.coca.coca_model import strip_checkpoint_prefixes
+    from embodied_captioning_b200.synth import state_dict_spec
+    spec = list(state_dict_spec(get_config("coca_tiny")))
+    plain = {k: i for i, k in enumerate(spec)}
+    for prefix in ("", "module.", "model.", "model.module.", "module.model."):
+        got = strip_checkpoint_prefixes({prefix + k: v for k, v in plain.items()})
+        assert got == plain, prefix
+    # a state dict that merely CONTAINS a `model.`-prefixed stray key is left alone (strict load reports it)
+    odd = dict(plain); odd["model.extra"] = 1
+    assert "model.extra" in strip_checkpoint_prefixes(odd)
+
+
+def test_eval_policy_float_boxes_round_like_pil_crop():
+    """evaluate_finetuned_model.py:33-37 passes raw CSV values to PIL `Image.crop` (round-half-even per coordinate)."""
+    from PIL import Image
+    H, W = 48, 64
+    img = np.random.default_rng(0).integers(0, 255, (H, W, 3), dtype=np.uint8)
+    im = Image.fromarray(img)
+    boxes = [[10.5, 11.5, 30.5, 40.49], [0.4, 3.5, 60.5, 45.5], [12.5, 2.5, 54.5, 38.5], [9.99, 10.0, 53.5, 37.500001],
+             [3, 4, 20, 30], [11.5, 12.5, 13.5, 14.5]]
+    rects, _ = tr.box_rects(boxes, H, W, tr.POLICY_EVAL)
+    for bb, r in zip(boxes, rects.tolist()):
+        b1 = [bb[0] - 10 if (bb[0] - 10) >= 0 else 0, bb[1] - 10 if (bb[1] - 10) >= 0 else bb[1],
+              bb[2] + 10 if (bb[2] + 10) <= im.size[0] else bb[2], bb[3] + 10 if (bb[3] + 10) <= im.size[1] else bb[3]]
+        crop = im.crop(b1)
+        assert crop.size == (r[2] - r[0], r[3] - r[1]), (bb, r)
+        assert po.crop_rect(po.POLICY_EVAL, bb, H, W)[0] == r
+        x1, y1, x2, y2 = r
+        ref = np.zeros((y2 - y1, x2 - x1, 3), np.uint8)
+        sx1, sy1, sx2, sy2 = max(x1, 0), max(y1, 0), min(x2, W), min(y2, H)
+        ref[sy1 - y1:sy2 - y1, sx1 - x1:sx2 - x1] = img[sy1:sy2, sx1:sx2]
+        assert (np.asarray(crop) == ref).all()
+
+
+def test_native_device_is_always_indexed():
+    from embodied_captioning_b200 import _native as nat
+    assert nat.cuda_device("cuda:3").index == 3
+    assert nat.cuda_device("cuda").index is not None and nat.cuda_device(None).index is not None
+    with pytest.raises(nat.NativeError):
+        nat.cuda_device("cpu")
