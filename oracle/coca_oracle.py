@@ -3,9 +3,16 @@
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may
 import this module; the product path never does.
 
-PARITY UNPINNED: the arithmetic of the reference lives in `open_clip_torch` (un-pinned in the
-reference's `requirements.txt:15`, not installed here, not vendored), so this file restates upstream
-open_clip's published modules as wired by the reference:
+PARITY STATUS: the arithmetic of the reference lives in `open_clip_torch` (un-pinned in the reference's
+`requirements.txt:15`, not installed here, not vendored), so `coca_model.py` cannot be imported and there are no
+reference outputs to compare with.  What CAN be pinned offline is pinned (tests/test_oracle_pins.py): every block of
+this file is compared to <= 1e-5 with the real `torch.nn.MultiheadAttention` (self, cross, and the pooler's kdim/vdim
+form), `nn.LayerNorm`, `nn.GELU`, `nn.Conv2d`, `nn.Embedding` assembled under upstream's parameter names (strict
+`load_state_dict` of the open_clip-layout state dict), and `generate` is compared token for token (ragged logits
+included) with the reference's own sampling statements executed on the real transformers `MinLengthLogitsProcessor` /
+`RepetitionPenaltyLogitsProcessor` / `TopKLogitsWarper` / `MaxLengthCriteria` and `torch.multinomial`.
+PARITY UNPINNED remains true only for open_clip's glue code (the order in which it calls those objects), restated here
+from upstream's published modules as wired by the reference:
 
   * wiring, `forward`, `generate(generation_type='top_k')`:
         experimenting_env/captioner/models/coca/coca_model.py:92-333
