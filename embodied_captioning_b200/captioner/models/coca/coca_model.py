@@ -14,6 +14,7 @@ raise instead of silently changing semantics.  There is no CPU execution path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -65,6 +66,7 @@ class CoCa(nn.Module):
         self._graph = False
         self._tc_attention = True
         self._chains = 0
+        self._absorbed = os.environ.get("EC_ABSORB", "1") != "0"     # A/B switch for probes
         self._dummy = nn.Parameter(torch.zeros(1), requires_grad=False)   # lets `.parameters()` work
 
     # ------------------------------------------------------------------ nn.Module protocol
@@ -126,6 +128,20 @@ class CoCa(nn.Module):
         nat.check(nat.lib().ec_model_set_option(self._handle, b"decode_graph", int(self._graph)), "ec_model_set_option")
         nat.check(nat.lib().ec_model_set_option(self._handle, b"tc_attention", int(self._tc_attention)))
         nat.check(nat.lib().ec_model_set_option(self._handle, b"decode_chains", self._chains))
+        nat.check(nat.lib().ec_model_set_option(self._handle, b"absorbed_cross", int(self._absorbed)))
+
+    def set_absorbed_cross(self, enabled: bool):
+        """Decoder cross-attention in the absorbed-projection form (default) or over per-layer K/V caches; the
+        absorbed weights are built when the weights are loaded, so switching it ON reloads them."""
+        enabled = bool(enabled)
+        if enabled == self._absorbed:
+            return
+        self._absorbed = enabled
+        if self._handle:
+            nat.check(nat.lib().ec_model_set_option(self._handle, b"absorbed_cross", int(enabled)))
+            if enabled and self._state_dict_ref is not None:
+                self.load_state_dict(self._state_dict_ref)
+            self._ws.pop("decode", None)
 
     def set_decode_graph(self, enabled: bool):
         self._graph = bool(enabled)

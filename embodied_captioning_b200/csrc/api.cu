@@ -71,6 +71,8 @@ int ec_model_set_option(ec_model* m, const char* key, int value) {
     return EC_OK;
   }
   if (!strcmp(key, "tc_attention")) { m->impl.use_tc_attention = value != 0; return EC_OK; }
+  // takes effect at the next ec_model_finalize (the absorbed weights are built there); switching it off works at once
+  if (!strcmp(key, "absorbed_cross")) { m->impl.absorbed_cross = value != 0; return EC_OK; }
   set_error("unknown option %s", key);
   return EC_ERR_INVALID;
 }
@@ -235,6 +237,7 @@ int ec_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64
 }
 
 int ec_check_watchdog(void* stream) {
+  EC_TRY(decode_cross_absorbed_check_watchdog(as_stream(stream)));
   EC_TRY(gemm_check_watchdog(as_stream(stream)));
   return attention_sm100_check_watchdog(as_stream(stream));
 }
@@ -257,6 +260,36 @@ int ec_attention_fused_qkv(const void* qkv, int64_t ld, int32_t q_col0, int32_t 
   a.batch = batch; a.heads = heads; a.sq = seq; a.skv = seq; a.head_dim = head_dim;
   a.scale = 1.0f / sqrtf((float)head_dim);
   return attention_full(a, as_stream(stream));
+}
+
+int ec_gemm_bf16_grouped(const void* a, int32_t lda, const void* w, int32_t ldw, int32_t m, int32_t n, int32_t k,
+                         int32_t group_cols, const float* bias, void* out, int32_t ldo, int32_t epilogue,
+                         int32_t use_simt_reference, void* stream) {
+  EC_REQUIRE(epilogue == 0 || epilogue == 2, EC_ERR_INVALID, "ec_gemm_bf16_grouped: epilogue %d", epilogue);
+  EC_REQUIRE(group_cols > 0, EC_ERR_INVALID, "ec_gemm_bf16_grouped: group_cols %d", group_cols);
+  GemmArgs g{};
+  g.A = reinterpret_cast<const bf16*>(a); g.lda = lda; g.W = reinterpret_cast<const bf16*>(w); g.ldw = ldw;
+  g.M = m; g.N = n; g.K = k; g.bias = bias; g.out = out; g.ldo = ldo; g.group_cols = group_cols;
+  if (use_simt_reference) return gemm_reference_simt(g, (GemmEpilogue)epilogue, as_stream(stream));
+  return gemm_bf16(g, (GemmEpilogue)epilogue, as_stream(stream));
+}
+
+size_t ec_packed_image_tokens_bytes(int32_t n, int32_t n_kv, int32_t width) {
+  return packed_image_tokens_elems(n, n_kv, width) * sizeof(bf16);
+}
+
+int ec_pack_image_tokens(const float* x, void* out, int32_t n, int32_t n_kv, int32_t width, int32_t normalize,
+                         void* stream) {
+  EC_REQUIRE(x && out, EC_ERR_INVALID, "ec_pack_image_tokens: null argument");
+  return pack_image_tokens(x, reinterpret_cast<bf16*>(out), n, n_kv, width, normalize != 0, as_stream(stream));
+}
+
+int ec_cross_attention_absorbed(const void* qp, const void* xn, void* ctx, int32_t batch, int32_t heads, int32_t width,
+                                int32_t n_kv, const uint8_t* finished, void* stream) {
+  EC_REQUIRE(qp && xn && ctx, EC_ERR_INVALID, "ec_cross_attention_absorbed: null argument");
+  return decode_cross_absorbed(reinterpret_cast<const bf16*>(qp), reinterpret_cast<const bf16*>(xn),
+                               reinterpret_cast<bf16*>(ctx), batch, heads, width, n_kv, finished, nullptr,
+                               as_stream(stream));
 }
 
 int64_t ec_launch_count(void) { return (int64_t)launch_count(); }

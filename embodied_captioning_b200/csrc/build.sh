@@ -7,7 +7,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 mkdir -p build
 pids=()
 rm -f build/gemm_sm100.o
-for f in common gemm_host layernorm attention attention_sm100 decode preprocess disagreement rasterize textenc model api; do
+for f in common gemm_host layernorm attention attention_sm100 decode cross_absorbed preprocess disagreement rasterize textenc model api; do
   if [ ! -f build/$f.o ] || [ $f.cu -nt build/$f.o ] || [ -n "$(find . -maxdepth 1 -name '*.cuh' -newer build/$f.o)" ] \
      || [ ../../include/ec_b200.h -nt build/$f.o ]; then
     ( $NVCC $FLAGS -c $f.cu -o build/$f.o || { rm -f build/$f.o; exit 1; } ) &

@@ -74,7 +74,8 @@ template <int BN, int EPI>
 static int launch_tile(const GemmArgs& a, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
   CUtensorMap ta, tw;
-  EC_TRY(make_tmap(&ta, a.A, a.M, a.K, a.lda, kBM));
+  const int groups = a.group_cols > 0 ? a.N / a.group_cols : 1;
+  EC_TRY(make_tmap(&ta, a.A, a.M, a.K * groups, a.lda, kBM));
   EC_TRY(make_tmap(&tw, a.W, a.N, a.K, a.ldw, BN));
   EpiParams p;
   p.M = a.M; p.N = a.N; p.bias = a.bias; p.residual = a.residual; p.ldr = a.ldr; p.out = a.out; p.ldo = a.ldo;
@@ -84,6 +85,7 @@ static int launch_tile(const GemmArgs& a, cudaStream_t stream) {
   p.ln_g = a.ln_gamma; p.ln_b = a.ln_beta; p.ln_out = a.ln_out; p.ld_ln = a.ld_ln; p.ln_cnt = a.ln_counters;
   p.ln_tiles_n = ceil_div(a.N, BN);
   p.pf_ptr = reinterpret_cast<const unsigned char*>(a.prefetch_ptr); p.pf_bytes = a.prefetch_bytes;
+  p.grp_cols = a.group_cols;
   const int tiles_m = ceil_div(a.M, kBM), tiles_n = ceil_div(a.N, BN);
   const int grid = std::min(tiles_m * tiles_n, num_sms());
   static bool attr_done[64] = {};   // per template instantiation and device
@@ -115,7 +117,7 @@ static int launch_pair_ew(const GemmArgs& a, cudaStream_t stream) {
   p.skip_flag = a.skip_flag;
   p.ln_g = a.ln_gamma; p.ln_b = a.ln_beta; p.ln_out = a.ln_out; p.ld_ln = a.ld_ln; p.ln_cnt = a.ln_counters;
   p.ln_tiles_n = ceil_div(a.N, BN);
-  p.pf_ptr = nullptr; p.pf_bytes = 0;
+  p.pf_ptr = nullptr; p.pf_bytes = 0; p.grp_cols = 0;
   const int tiles_m = ceil_div(a.M, 2 * kBM), tiles_n = ceil_div(a.N, BN);
   const int clusters = std::min(tiles_m * tiles_n, num_sms() / 2);
   static bool attr_done[64] = {};   // per template instantiation and device
@@ -153,6 +155,19 @@ static bool use_pair_kernel(const GemmArgs& a) {
 
 template <int EPI>
 static int launch_epi(const GemmArgs& a, cudaStream_t stream) {
+  if constexpr (EPI == EPI_BF16 || EPI == EPI_F32) {
+    if (a.group_cols > 0) {        // grouped GEMM: 1-CTA kernel, tiles must not straddle two groups
+      int bn = a.bn_hint;
+      if (bn == 0) bn = (a.group_cols % 256 == 0) ? 256 : (a.group_cols % 128 == 0 ? 128 : 64);
+      EC_REQUIRE(a.group_cols % bn == 0, EC_ERR_UNSUPPORTED, "grouped GEMM: tile width %d does not divide group_cols %d",
+                 bn, a.group_cols);
+      if (bn == 256) return launch_tile<256, EPI>(a, stream);
+      if (bn == 128) return launch_tile<128, EPI>(a, stream);
+      if (bn == 64) return launch_tile<64, EPI>(a, stream);
+      set_error("grouped GEMM: unsupported tile width %d", bn);
+      return EC_ERR_UNSUPPORTED;
+    }
+  }
   if (use_pair_kernel(a)) return launch_pair<256, EPI>(a, stream);
   if constexpr (EPI == EPI_ARGMAX) {
     return launch_tile<256, EPI>(a, stream);
@@ -226,6 +241,14 @@ static int gemm_dispatch(const GemmArgs& a, GemmEpilogue epi, cudaStream_t strea
   // K may be ragged (TMA zero-fills the box beyond K); only row strides need 16-byte alignment
   EC_REQUIRE(a.N % 8 == 0, EC_ERR_UNSUPPORTED, "GEMM needs N to be a multiple of 8 (N=%d)", a.N);
   EC_REQUIRE(a.lda >= a.K && a.ldw >= a.K, EC_ERR_INVALID, "GEMM row strides shorter than K");
+  if (a.group_cols > 0) {
+    EC_REQUIRE(epi == EPI_BF16 || epi == EPI_F32, EC_ERR_UNSUPPORTED, "grouped GEMM supports the plain epilogues only");
+    EC_REQUIRE(a.N % a.group_cols == 0 && a.K % kBK == 0 && a.group_cols % 64 == 0, EC_ERR_UNSUPPORTED,
+               "grouped GEMM: N %d, group_cols %d, K %d", a.N, a.group_cols, a.K);
+    EC_REQUIRE((long long)a.lda >= (long long)a.K * (a.N / a.group_cols), EC_ERR_INVALID,
+               "grouped GEMM: A row stride %d shorter than groups * K", a.lda);
+    EC_REQUIRE(a.ln_out == nullptr, EC_ERR_UNSUPPORTED, "grouped GEMM has no fused LayerNorm tail");
+  }
   EC_REQUIRE(a.A && a.W, EC_ERR_INVALID, "GEMM null operand");
   if (epi != EPI_ARGMAX) {
     EC_REQUIRE(a.out != nullptr && a.ldo % 8 == 0, EC_ERR_INVALID, "GEMM output null or ldo %% 8 != 0");
@@ -277,7 +300,8 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, int lda, const bf16
   const int row = blockIdx.y;
   if (col >= N || row >= M) return;
   float acc = 0.f;
-  for (int k = 0; k < K; ++k) acc += __bfloat162float(A[(size_t)row * lda + k]) * __bfloat162float(W[(size_t)col * ldw + k]);
+  const size_t a0 = (size_t)row * lda + (p.grp_cols > 0 ? (size_t)(col / p.grp_cols) * K : 0);
+  for (int k = 0; k < K; ++k) acc += __bfloat162float(A[a0 + k]) * __bfloat162float(W[(size_t)col * ldw + k]);
   if (p.bias) acc += p.bias[col];
   if (epi == EPI_BF16) reinterpret_cast<bf16*>(p.out)[(size_t)row * p.ldo + col] = __float2bfloat16_rn(acc);
   else if (epi == EPI_BF16_GELU) reinterpret_cast<bf16*>(p.out)[(size_t)row * p.ldo + col] = __float2bfloat16_rn(gelu_erf(acc));
@@ -293,7 +317,7 @@ int gemm_reference_simt(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream
   p.logits = a.logits; p.ld_logits = a.ld_logits; p.logits_step_stride = a.logits_step_stride; p.part_val = a.part_val; p.part_idx = a.part_idx;
   p.n_parts = a.n_parts; p.eos_col = a.eos_col; p.cur_len = a.cur_len; p.min_len = a.min_len; p.skip_flag = nullptr;
   p.ln_g = nullptr; p.ln_b = nullptr; p.ln_out = nullptr; p.ld_ln = 0; p.ln_cnt = nullptr; p.ln_tiles_n = 0;
-  p.pf_ptr = nullptr; p.pf_bytes = 0;
+  p.pf_ptr = nullptr; p.pf_bytes = 0; p.grp_cols = a.group_cols;
   dim3 grid(ceil_div(a.N, 128), a.M);
   gemm_simt_kernel<<<grid, 128, 0, stream>>>(a.A, a.lda, a.W, a.ldw, a.M, a.N, a.K, p, (int)epi);
   EC_POST_LAUNCH();

@@ -246,6 +246,7 @@ struct EpiParams {
   // L2 prefetch of the NEXT GEMM's weights (decoder steps: weights cycle through L2 once per step, so every K panel
   // would otherwise arrive at HBM latency); issued by warp 2 once it has allocated the tensor memory
   const unsigned char* pf_ptr; unsigned long long pf_bytes;
+  int grp_cols;     // grouped GEMM: output columns per group (0 = plain GEMM); see GemmArgs::group_cols
 };
 
 // One 32 x 32 chunk.  kFull = the whole chunk lies inside [M, N]: no per-element bound predicates (the interior
@@ -572,10 +573,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     __syncwarp();
     const int m_blk = (int)blockIdx.x / tiles_n, n_blk = (int)blockIdx.x % tiles_n;
+    const int a_k0 = (p.grp_cols > 0) ? (n_blk * BN / p.grp_cols) * K : 0;     // grouped GEMM: this tile's column slab of A
     for (int g = 0; g < pre; ++g) {               // warp-uniform loop, elected lane issues (see the MMA warp)
       if (ptx::elect_one()) {
         ptx::mbar_expect_tx(full_bar(g), Cfg::kStageBytes);
-        ptx::tma_load_2d(smem_a0 + g * Cfg::kABytes, &tmap_a, g * kBK, m_blk * kBM, full_bar(g));
+        ptx::tma_load_2d(smem_a0 + g * Cfg::kABytes, &tmap_a, a_k0 + g * kBK, m_blk * kBM, full_bar(g));
         ptx::tma_load_2d(smem_b0 + g * Cfg::kBBytes, &tmap_w, g * kBK, n_blk * BN, full_bar(g));
       }
       __syncwarp();
@@ -637,6 +639,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int g = 0;                                  // running k-block index of this CTA over all its tiles
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+        const int a_k0 = (p.grp_cols > 0) ? (n_blk * BN / p.grp_cols) * K : 0;
         for (int kb = 0; kb < num_kb; ++kb, ++g) {
           if ((g & 1) != w || g < pre) continue;      // the first `pre` k-blocks were issued in the prologue
           const int stage = g % Cfg::kStages;
@@ -646,7 +649,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           if (ptx::elect_one()) {
             ptx::mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            ptx::tma_load_2d(smem_a0 + stage * Cfg::kABytes, &tmap_a, kb * kBK, m_blk * kBM, full_bar(stage));
+            ptx::tma_load_2d(smem_a0 + stage * Cfg::kABytes, &tmap_a, a_k0 + kb * kBK, m_blk * kBM, full_bar(stage));
             ptx::tma_load_2d(smem_b0 + stage * Cfg::kBBytes, &tmap_w, kb * kBK, n_blk * BN, full_bar(stage));
           }
           __syncwarp();

@@ -40,6 +40,11 @@ struct GemmArgs {
   const float* ln_gamma; const float* ln_beta; bf16* ln_out; int ld_ln; int* ln_counters;
   // optional: bring [prefetch_ptr, +prefetch_bytes) into L2 while this GEMM runs (the next GEMM's weights; 1-CTA kernel)
   const void* prefetch_ptr; size_t prefetch_bytes;
+  // Grouped (block-diagonal) form, group_cols > 0:  out[m, n] = sum_k A[m, (n / group_cols) * K + k] * W[n, k]  -- every
+  // group of `group_cols` output columns reads its own K-wide column slab of A (A is [M, (N / group_cols) * K]).  Used
+  // by the absorbed cross-attention of the decoder (per-head projections).  K % 64 == 0; 1-CTA kernel, tile width
+  // `bn_hint` (0 = the widest of 256 / 128 / 64 that divides group_cols).
+  int group_cols; int bn_hint;
 };
 
 // true when gemm_bf16 runs this shape on the CTA-pair kernel (whose fused LayerNorm tail needs no inter-CTA sync)

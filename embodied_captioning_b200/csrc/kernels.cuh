@@ -72,6 +72,20 @@ int decode_self_attention(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out
 int decode_cross_attention(const bf16* q, const bf16* kv, bf16* out, int batch, int heads, int head_dim, int n_kv,
                            const unsigned char* finished, const DecodeState* st, cudaStream_t stream);
 
+// ---- cross_absorbed.cu: absorbed-projection cross-attention (keys = values = the normalised image tokens) ---------
+// qp bf16 [B, heads*T] (absorbed queries W_k,h^T q_h / sqrt(d)), xn bf16 = the crop's image tokens in the PACKED layout
+// of pack_image_tokens (shared by all layers), ctx bf16 [B, heads*T] (per-head softmax-weighted sums of the token rows).
+// T in {256, 512, 768}, heads <= 16.
+size_t packed_image_tokens_elems(int n, int n_kv, int width);
+// x f32 [n, n_kv, T] -> packed bf16 (32-row chunks, rows of T + 8 elements, zero padding); normalize: (x - mean) * rstd
+int pack_image_tokens(const float* x, bf16* out, int n, int n_kv, int width, bool normalize, cudaStream_t stream);
+bool decode_cross_absorbed_supported(int width, int heads, int head_dim, int n_kv);
+int decode_cross_absorbed(const bf16* qp, const bf16* xn, bf16* ctx, int batch, int heads, int width, int n_kv,
+                          const unsigned char* finished, const DecodeState* st, cudaStream_t stream);
+// wk_abs [heads*T, head_dim] = per-head transpose of the K projection rows wk [heads*head_dim, T], times `scale`
+int absorb_k_weights(const bf16* wk, bf16* out, int heads, int head_dim, int width, float scale, cudaStream_t stream);
+int decode_cross_absorbed_check_watchdog(cudaStream_t stream);
+
 // reduce the arg-max partials of the vocab GEMM, apply the generate() token rules (coca_model.py:304-322)
 int decode_select(const float* part_val, const int* part_idx, int n_parts, int* tokens, int ld_tokens,
                   unsigned char* finished, int batch, int seq_len, int eos, int pad, DecodeState* st,

@@ -74,6 +74,8 @@ Model::Model(const ec_config& c, int dev) : cfg(c), device(dev) {
   prefetch_weights = env_pf != 0;
   static const int env_lnkv = [] { const char* e = getenv("EC_SHARED_LNKV"); return e ? atoi(e) : 1; }();
   shared_lnkv = env_lnkv != 0;
+  static const int env_abs = [] { const char* e = getenv("EC_ABSORB"); return e ? atoi(e) : 1; }();
+  absorbed_cross = env_abs != 0;
   static const int env_fuse = [] { const char* e = getenv("EC_FUSE_LN"); return e ? atoi(e) : 0; }();
   if (env_fuse == 0) fuse_ln = false;
   // image tower: the CTA-local tail (no atomics, contiguous tile schedule) also loses -- the epilogue warps that run it
@@ -201,6 +203,12 @@ int Model::set_tensor(const char* name, const float* h, int64_t numel) {
   return EC_ERR_INVALID;
 }
 
+bool Model::use_absorbed() const {
+  return absorbed_cross && shared_lnkv && !dcross.empty() && wk_abs.size() == dcross.size() && wk_abs[0] != nullptr &&
+         decode_cross_absorbed_supported(cfg.text_width, cfg.mm_heads, cfg.text_width / std::max(cfg.mm_heads, 1),
+                                         cfg.n_queries - 1);
+}
+
 static bool block_complete(const Block& b, bool cross) {
   return b.ln1_g && b.ln1_b && b.ln2_g && b.ln2_b && b.w_qkv && b.b_qkv && b.w_out && b.b_out && b.w_fc1 && b.b_fc1 &&
          b.w_fc2 && b.b_fc2 && (!cross || (b.lnkv_g && b.lnkv_b));
@@ -256,6 +264,18 @@ int Model::finalize(cudaStream_t stream) {
       const Block& b = dcross[l];
       rc = fold_layernorm_into_linear(b.w_qkv + (size_t)T * T, b.b_qkv + T, b.lnkv_g, b.lnkv_b, wkv_fold[l], bkv_fold[l],
                                       2 * T, T, stream);
+    }
+    // absorbed K projections: wk_abs[l][(h*T + i), d] = wkv_fold[l][(h*64 + d), i] / sqrt(64)
+    const int hd = T / std::max(cfg.mm_heads, 1);
+    if (rc == EC_OK && absorbed_cross && decode_cross_absorbed_supported(T, cfg.mm_heads, hd, cfg.n_queries - 1)) {
+      wk_abs.resize(dcross.size(), nullptr);
+      for (size_t l = 0; l < dcross.size() && rc == EC_OK; ++l) {
+        if (wk_abs[l] == nullptr) {
+          if (cudaMalloc(&wk_abs[l], (size_t)T * T * sizeof(bf16)) != cudaSuccess) { rc = EC_ERR_CUDA; break; }
+          owned.push_back(wk_abs[l]);
+        }
+        rc = absorb_k_weights(wkv_fold[l], wk_abs[l], cfg.mm_heads, hd, T, 1.0f / sqrtf((float)hd), stream);
+      }
     }
   }
   cudaError_t e = cudaStreamSynchronize(stream);
@@ -421,6 +441,7 @@ int Model::encode_image(const bf16* x, int n, float* latent, float* embs, void* 
 struct DecodeWs {
   bf16* ln_kv; bf16* cross_kv; bf16* tk; bf16* tv; bf16* dk; bf16* dv;
   float* x; bf16* ln; bf16* qkv; bf16* att; bf16* fc1; bf16* q;
+  bf16* qp; bf16* ctx;   // absorbed cross-attention: per-head absorbed queries / contexts [n, heads*T]
   float* part_val; int* part_idx; unsigned char* finished; DecodeState* st; int* tokens_tf;
   int* ln_cnt;           // fused-LayerNorm row-block counters of this chain
   size_t cache_layer;    // elements between the self-K/V caches of consecutive layers (whole batch)
@@ -434,9 +455,11 @@ static DecodeWs slice_rows(const Model& m, const DecodeWs& w, int r0, int seq_le
   const size_t T = c.text_width, NK = c.n_queries - 1, L = seq_len, r = (size_t)r0;
   const size_t parts = (size_t)gemm_argmax_parts(c.vocab_size);
   DecodeWs v = w;
-  v.ln_kv += r * NK * T; v.cross_kv += r * NK * 2 * T;
+  v.ln_kv += m.use_absorbed() ? packed_image_tokens_elems(r0, (int)NK, (int)T) : r * NK * T;
+  v.cross_kv += r * NK * 2 * T;
   v.tk += r * L * T; v.tv += r * L * T; v.dk += r * L * T; v.dv += r * L * T;
   v.x += r * T; v.ln += r * T; v.qkv += r * 3 * T; v.att += r * T; v.fc1 += r * 4 * T; v.q += r * T;
+  v.qp += r * (size_t)c.mm_heads * T; v.ctx += r * (size_t)c.mm_heads * T;
   v.part_val += r * parts; v.part_idx += r * parts; v.finished += r; v.tokens_tf += r * L;
   v.st += chain;
   v.ln_cnt = m.ln_counters + kLnCountersEncoder + chain * kLnCountersPerChain;
@@ -449,8 +472,9 @@ static DecodeWs carve_decode(const Model& m, void* ws, int n, int seq_len) {
   const size_t L = seq_len;   // cache length (positions 0 .. seq_len-2 are ever written)
   Bump b(ws);
   DecodeWs w;
-  w.ln_kv = b.take<bf16>((size_t)n * NK * T);
-  w.cross_kv = b.take<bf16>((size_t)c.mm_layers * n * NK * 2 * T);
+  const bool absorbed = m.use_absorbed();     // no per-layer K / V caches: the decoder streams ln_kv itself (packed layout)
+  w.ln_kv = b.take<bf16>(absorbed ? packed_image_tokens_elems(n, (int)NK, (int)T) : (size_t)n * NK * T);
+  w.cross_kv = b.take<bf16>(absorbed ? 0 : (size_t)c.mm_layers * n * NK * 2 * T);
   w.tk = b.take<bf16>((size_t)c.text_layers * n * L * T);
   w.tv = b.take<bf16>((size_t)c.text_layers * n * L * T);
   w.dk = b.take<bf16>((size_t)c.mm_layers * n * L * T);
@@ -461,6 +485,8 @@ static DecodeWs carve_decode(const Model& m, void* ws, int n, int seq_len) {
   w.att = b.take<bf16>((size_t)n * T);
   w.fc1 = b.take<bf16>((size_t)n * 4 * T);
   w.q = b.take<bf16>((size_t)n * T);
+  w.qp = b.take<bf16>(absorbed ? (size_t)n * c.mm_heads * T : 0);
+  w.ctx = b.take<bf16>(absorbed ? (size_t)n * c.mm_heads * T : 0);
   const size_t parts = (size_t)gemm_argmax_parts(c.vocab_size);
   w.part_val = b.take<float>((size_t)n * parts);
   w.part_idx = b.take<int>((size_t)n * parts);
@@ -504,8 +530,9 @@ int Model::self_block(const Block& b, const DecodeWs& w, bf16* kc, bf16* vc, int
   return EC_OK;
 }
 
-int Model::cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int n, bool ln1_done, const float* next_g,
-                       const float* next_b, Prefetch next_pf, cudaStream_t s) {
+// `layer` >= 0: absorbed-projection cross-attention with that layer's absorbed weights (kv unused); -1: K/V cache `kv`
+int Model::cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int layer, int n, bool ln1_done,
+                       const float* next_g, const float* next_b, Prefetch next_pf, cudaStream_t s) {
   const int T = cfg.text_width, NK = cfg.n_queries - 1;
   const int* skip = &w.st->done;
   const bool fuse = decoder_fuse(n);
@@ -514,7 +541,22 @@ int Model::cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int n,
   const Prefetch none;
   EC_TRY(linear(w.ln, T, b.w_qkv, T, b.b_qkv, n, T, T, w.q, T, EPI_BF16, nullptr, 0, skip, s, nullptr,
                 prefetch_weights ? Prefetch{b.w_out, TT} : none));   // q rows only
-  EC_TRY(decode_cross_attention(w.q, kv, w.att, n, cfg.mm_heads, T / cfg.mm_heads, NK, w.finished, w.st, s));
+  if (layer >= 0) {
+    // absorbed form (cross_absorbed.cu): q' = per-head W_k^T q / 8 (grouped GEMM, K = 64), one pass over the normalised
+    // image tokens, then the per-head V projection of the contexts (grouped GEMM, K = T) -> w.att
+    const int H = cfg.mm_heads, hd = T / H;
+    GemmArgs gq{};
+    gq.A = w.q; gq.lda = T; gq.W = wk_abs[layer]; gq.ldw = hd; gq.M = n; gq.N = H * T; gq.K = hd;
+    gq.out = w.qp; gq.ldo = H * T; gq.skip_flag = skip; gq.group_cols = T;
+    EC_TRY(gemm_bf16(gq, EPI_BF16, s));
+    EC_TRY(decode_cross_absorbed(w.qp, w.ln_kv, w.ctx, n, H, T, NK, w.finished, w.st, s));
+    GemmArgs gv{};
+    gv.A = w.ctx; gv.lda = H * T; gv.W = wkv_fold[layer] + (size_t)T * T; gv.ldw = T; gv.M = n; gv.N = T; gv.K = T;
+    gv.bias = bkv_fold[layer] + T; gv.out = w.att; gv.ldo = T; gv.skip_flag = skip; gv.group_cols = hd; gv.bn_hint = 64;
+    EC_TRY(gemm_bf16(gv, EPI_BF16, s));
+  } else {
+    EC_TRY(decode_cross_attention(w.q, kv, w.att, n, cfg.mm_heads, T / cfg.mm_heads, NK, w.finished, w.st, s));
+  }
   FusedLn ln2{b.ln2_g, b.ln2_b, fuse ? w.ln : nullptr, T, w.ln_cnt};
   EC_TRY(linear(w.att, T, b.w_out, T, b.b_out, n, T, T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &ln2,
                 prefetch_weights ? Prefetch{b.w_fc1, 4 * TT} : none));
@@ -548,7 +590,8 @@ int Model::chain_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int 
                       fuse && (l > 0 || cfg.text_layers > 0), dcross[l].ln1_g, dcross[l].ln1_b,
                       Prefetch{dcross[l].w_qkv, TTb}, s));
     const bool last = (l + 1 == cfg.mm_layers);
-    EC_TRY(cross_block(dcross[l], w, w.cross_kv + l * w.cross_layer, n, fuse, last ? ln_final_g : dself[l + 1].ln1_g,
+    EC_TRY(cross_block(dcross[l], w, w.cross_kv + l * w.cross_layer, use_absorbed() ? l : -1, n, fuse,
+                       last ? ln_final_g : dself[l + 1].ln1_g,
                        last ? ln_final_b : dself[l + 1].ln1_b,
                        last ? Prefetch{tblocks.empty() ? nullptr : tblocks[0].w_qkv, 3 * TTb} : Prefetch{dself[l + 1].w_qkv, 3 * TTb},
                        s));
@@ -595,6 +638,8 @@ int Model::prefill_cross_kv(const DecodeWs& w, const float* embs, int n, cudaStr
   const int rows = n * NK;
   if (shared_lnkv && (int)wkv_fold.size() == cfg.mm_layers) {
     // one normalisation of the image tokens for all layers; gamma / beta sit in the pre-multiplied weights (finalize)
+    // absorbed form: the decoder attends over the normalised tokens themselves, staged in the packed layout
+    if (use_absorbed()) return pack_image_tokens(embs, w.ln_kv, n, NK, T, true, s);
     EC_TRY(layernorm(embs, T, unit_gamma, zero_beta, w.ln_kv, T, true, rows, T, nullptr, s));
     for (int l = 0; l < cfg.mm_layers; ++l)
       EC_TRY(linear(w.ln_kv, T, wkv_fold[l], T, bkv_fold[l], rows, 2 * T, T, w.cross_kv + (size_t)l * rows * 2 * T,

@@ -36,6 +36,12 @@ struct Model {
   bool shared_lnkv = true;
   std::vector<bf16*> wkv_fold;
   std::vector<float*> bkv_fold;
+  // absorbed-projection cross-attention (cross_absorbed.cu): the decoder streams the normalised image tokens instead of
+  // per-layer K / V caches; wk_abs[l] = per-head transposed, pre-scaled K projection [heads*T, 64] (option
+  // "absorbed_cross" / EC_ABSORB=0: off -> K/V caches as in round 1)
+  bool absorbed_cross = true;
+  std::vector<bf16*> wk_abs;
+  bool use_absorbed() const;
   float *unit_gamma = nullptr, *zero_beta = nullptr;
   int* ln_counters = nullptr;      // row-block arrival counters of the fused tails (zero between launches)
   bool use_tc_attention = false;   // tcgen05/TMEM attention for the ViT blocks (option "tc_attention")
@@ -92,7 +98,7 @@ struct Model {
   int set_block_tensor(Block& b, int width, const char* leaf, const char* name, const float* h, int64_t numel);
   int self_block(const Block& b, const DecodeWs& w, bf16* kc, bf16* vc, int n, int max_len, int heads, bool ln1_done,
                  const float* next_g, const float* next_b, Prefetch next_pf, cudaStream_t s);
-  int cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int n, bool ln1_done, const float* next_g,
+  int cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int layer, int n, bool ln1_done, const float* next_g,
                   const float* next_b, Prefetch next_pf, cudaStream_t s);
   int chain_rows(int n) const;
   int chain_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len,

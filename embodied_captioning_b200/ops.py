@@ -44,6 +44,50 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     return out
 
 
+def gemm_grouped(a: torch.Tensor, w: torch.Tensor, group_cols: int, bias: Optional[torch.Tensor] = None,
+                 epilogue: int = EPI_BF16, simt_reference: bool = False) -> torch.Tensor:
+    """out[m, n] = sum_k a[m, (n // group_cols) * K + k] * w[n, k] (+ bias): a [M, groups*K], w [N, K] bf16."""
+    _check_dev(a, w, bias)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.stride(1) == 1 and w.stride(1) == 1
+    M, N, K = a.shape[0], w.shape[0], w.shape[1]
+    assert N % group_cols == 0 and a.shape[1] == (N // group_cols) * K
+    out = torch.empty((M, N), device=a.device, dtype=torch.bfloat16 if epilogue == EPI_BF16 else torch.float32)
+    with torch.cuda.device(a.device):
+        nat.check(nat.lib().ec_gemm_bf16_grouped(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K,
+                                                 group_cols, nat.ptr(bias), out.data_ptr(), out.stride(0), epilogue,
+                                                 int(simt_reference), _stream(a)), "ec_gemm_bf16_grouped")
+    return out
+
+
+def pack_image_tokens(x: torch.Tensor, normalize: bool = False) -> torch.Tensor:
+    """x f32 [B, n_kv, T] -> packed bf16 buffer (32-row chunks, rows of T + 8 elements, zero padded) that
+    `cross_attention_absorbed` streams; normalize = LayerNorm without affine (eps 1e-5)."""
+    _check_dev(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3
+    B, n_kv, T = x.shape
+    lib = nat.lib()
+    out = torch.empty((lib.ec_packed_image_tokens_bytes(B, n_kv, T) // 2,), device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        nat.check(lib.ec_pack_image_tokens(x.data_ptr(), out.data_ptr(), B, n_kv, T, int(normalize), _stream(x)),
+                  "ec_pack_image_tokens")
+    return out
+
+
+def cross_attention_absorbed(qp: torch.Tensor, xn_packed: torch.Tensor, n_kv: int,
+                             finished: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qp bf16 [B, H, T], xn_packed = pack_image_tokens(...) -> ctx bf16 [B, H, T]: softmax(qp xn^T) xn per crop."""
+    _check_dev(qp, xn_packed, finished)
+    assert qp.dtype == torch.bfloat16 and xn_packed.dtype == torch.bfloat16 and qp.is_contiguous()
+    B, H, T = qp.shape
+    assert xn_packed.numel() * 2 == nat.lib().ec_packed_image_tokens_bytes(B, n_kv, T)
+    ctx = torch.zeros_like(qp) if out is None else out
+    with torch.cuda.device(qp.device):
+        nat.check(nat.lib().ec_cross_attention_absorbed(qp.data_ptr(), xn_packed.data_ptr(), ctx.data_ptr(), B, H, T,
+                                                        n_kv, nat.ptr(finished), _stream(qp)),
+                  "ec_cross_attention_absorbed")
+    return ctx
+
+
 def gemm_argmax(a: torch.Tensor, w: torch.Tensor, want_logits: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     _check_dev(a, w)
     M, K = a.shape

@@ -171,7 +171,26 @@ int ec_attention(const void* q_dev, int64_t q_bs, int64_t q_rs, const void* k_de
 int ec_attention_fused_qkv(const void* qkv_dev, int64_t ld, int32_t q_col0, int32_t k_col0, int32_t v_col0,
                            void* out_dev, int64_t o_bs, int64_t o_rs, int32_t batch, int32_t heads, int32_t seq,
                            int32_t head_dim, int32_t impl, void* stream);
-int ec_check_watchdog(void* stream);   /* EC_ERR_TIMEOUT if a tcgen05 pipeline wait ever timed out */
+/* grouped (block-diagonal) GEMM: out[m, n] = sum_k A[m, (n / group_cols) * k_per_group + k] * W[n, k]; epilogue 0 or 2.
+ * The decoder's absorbed cross-attention uses it for the per-head projections on either side of
+ * ec_cross_attention_absorbed (reference: the k/v in-projections of text_decoder.cross_attn.{l}.attn, an
+ * nn.MultiheadAttention, coca_model.py:130-135 -> upstream MultimodalTransformer). */
+int ec_gemm_bf16_grouped(const void* a_bf16_dev, int32_t lda, const void* w_bf16_dev, int32_t ldw, int32_t m, int32_t n,
+                         int32_t k_per_group, int32_t group_cols, const float* bias_dev, void* out_dev, int32_t ldo,
+                         int32_t epilogue, int32_t use_simt_reference, void* stream);
+/* image tokens in the layout the absorbed cross-attention streams: per crop ceil(n_kv / 32) chunks of 32 rows, each row
+ * `width` bf16 + 8 zero elements, rows past n_kv zero; normalize != 0 applies (x - mean) * rstd (eps 1e-5), i.e. the
+ * ln_1_kv LayerNorm without its affine part (text_decoder.cross_attn.{l}.ln_1_kv; gamma / beta are folded into the
+ * projection weights when the model is finalized).  x f32 [n, n_kv, width]. */
+size_t ec_packed_image_tokens_bytes(int32_t n, int32_t n_kv, int32_t width);
+int ec_pack_image_tokens(const float* x_dev, void* out_bf16_dev, int32_t n, int32_t n_kv, int32_t width,
+                         int32_t normalize, void* stream);
+/* single-query attention whose keys AND values are the rows of xn (the packed image tokens of a crop):
+ * ctx[b, h, :] = sum_j softmax_j(qp[b, h, :] . xn[b, j, :]) xn[b, j, :].  qp, ctx bf16 [batch, heads * width];
+ * xn = ec_pack_image_tokens output; width in {256, 512, 768}, heads <= 16; finished (nullable) uint8 [batch] skips rows. */
+int ec_cross_attention_absorbed(const void* qp_dev, const void* xn_dev, void* ctx_dev, int32_t batch, int32_t heads,
+                                int32_t width, int32_t n_kv, const uint8_t* finished_dev, void* stream);
+int ec_check_watchdog(void* stream);   /* EC_ERR_TIMEOUT if a tcgen05 / bulk-copy pipeline wait ever timed out */
 
 /* ---- measurement hooks used by bench.py */
 int64_t ec_launch_count(void);          /* kernels launched by this library so far (graph replays included) */

@@ -178,3 +178,70 @@ def test_gemm_fused_layernorm_tail(device, M, N, K):
         assert torch.equal(out, plain)
         assert torch.equal(ln, ref_ln)
         assert int(cnt.abs().sum()) == 0
+
+
+# ------------------------------------------------------------------------------- absorbed cross-attention (decoder)
+@pytest.mark.parametrize("M,heads,T,hd", [(1024, 12, 768, 64), (300, 8, 512, 64), (7, 4, 256, 64)])
+def test_grouped_gemm_per_head_projections(device, M, heads, T, hd):
+    """The two grouped GEMMs on either side of the absorbed cross-attention, vs plain fp32 per-head matmuls."""
+    # q' = per-head W_k^T q: A [M, heads*hd], groups of T output columns, K = hd
+    q = _rand_bf16((M, heads * hd), device, seed=11)
+    wk_abs = _rand_bf16((heads * T, hd), device, hd ** -0.5, seed=12)
+    out = ops.gemm_grouped(q, wk_abs, group_cols=T)
+    ref = torch.einsum("mhd,htd->mht", q.float().view(M, heads, hd), wk_abs.float().view(heads, T, hd)).reshape(M, heads * T)
+    assert (out.float() - ref).abs().max().item() < 0.05
+    simt = ops.gemm_grouped(q, wk_abs, group_cols=T, epilogue=ops.EPI_F32, simt_reference=True)
+    assert (simt - ref).abs().max().item() < 1e-3
+    # att = per-head W_v c + b_v: A [M, heads*T], groups of hd output columns, K = T
+    c = _rand_bf16((M, heads * T), device, seed=13)
+    wv = _rand_bf16((heads * hd, T), device, T ** -0.5, seed=14)
+    bias = torch.randn(heads * hd, device=device)
+    out2 = ops.gemm_grouped(c, wv, group_cols=hd, bias=bias, epilogue=ops.EPI_F32)
+    ref2 = torch.einsum("mht,hdt->mhd", c.float().view(M, heads, T), wv.float().view(heads, hd, T)).reshape(M, heads * hd) + bias
+    assert (out2 - ref2).abs().max().item() < 2e-3 * max(1.0, ref2.abs().max().item())
+    ops.check_watchdog(device)
+
+
+@pytest.mark.parametrize("B,heads,T,n_kv", [(5, 12, 768, 255), (300, 12, 768, 255), (33, 8, 512, 255), (9, 4, 256, 255),
+                                            (3, 12, 768, 31), (4, 12, 768, 64), (2, 4, 256, 1)])
+def test_cross_attention_absorbed_matches_fp32(device, B, heads, T, n_kv):
+    """ctx = softmax(qp xn^T) xn per crop and head (keys = values = the normalised image tokens), persistent over crops
+    (B > 148 wraps the CTA loop), ragged last chunk (n_kv % 32 != 0)."""
+    qp = _rand_bf16((B, heads, T), device, 3.0 * T ** -0.5, seed=21)      # logits of O(3): a peaked softmax
+    xn = _rand_bf16((B, n_kv, T), device, seed=22)
+    ctx = ops.cross_attention_absorbed(qp, ops.pack_image_tokens(xn.float()), n_kv)
+    ops.check_watchdog(device)
+    s = torch.einsum("bht,bjt->bhj", qp.float(), xn.float())
+    ref = torch.einsum("bhj,bjt->bht", torch.softmax(s, dim=-1), xn.float())
+    err = (ctx.float() - ref).abs().max().item()
+    assert err < 0.03, err
+    cos = torch.nn.functional.cosine_similarity(ctx.float().flatten(1), ref.flatten(1)).min().item()
+    assert cos > 0.9999, cos
+
+
+def test_cross_attention_absorbed_skips_finished_rows(device):
+    B, heads, T, n_kv = 200, 12, 768, 255
+    qp = _rand_bf16((B, heads, T), device, 2.0 * T ** -0.5, seed=31)
+    xn = _rand_bf16((B, n_kv, T), device, seed=32)
+    fin = (torch.arange(B, device=device) % 3 == 1).to(torch.uint8)
+    packed = ops.pack_image_tokens(xn.float())
+    full = ops.cross_attention_absorbed(qp, packed, n_kv)
+    part = ops.cross_attention_absorbed(qp, packed, n_kv, finished=fin)
+    ops.check_watchdog(device)
+    live = fin == 0
+    assert torch.equal(part[live], full[live])
+    assert part[~live].abs().max().item() == 0.0          # untouched (the wrapper zero-fills its output)
+
+
+@pytest.mark.parametrize("B,n_kv,T", [(3, 255, 768), (5, 31, 512), (2, 64, 256)])
+def test_pack_image_tokens_layout_and_normalisation(device, B, n_kv, T):
+    """Packed layout: 32-row chunks, rows of T + 8 elements, zero padding; normalize = LayerNorm without affine."""
+    x = torch.randn((B, n_kv, T), device=device) * 3 + 1.5
+    rows = (n_kv + 31) // 32 * 32
+    for normalize in (False, True):
+        p = ops.pack_image_tokens(x, normalize=normalize).view(B, rows, T + 8).float()
+        ref = torch.nn.functional.layer_norm(x, (T,), eps=1e-5) if normalize else x
+        assert (p[:, :n_kv, :T] - ref).abs().max().item() < 0.02 * ref.abs().max().item()
+        assert p[:, :n_kv, T:].abs().max().item() == 0.0
+        if rows > n_kv:
+            assert p[:, n_kv:].abs().max().item() == 0.0

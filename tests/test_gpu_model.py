@@ -321,3 +321,32 @@ def test_greedy_sequences_identical_on_99_percent_with_trained_like_head(device,
     rk, rs, rc = do.instance_disagreement(lat_ref.numpy(), ids, mode="full")
     assert k.cpu().tolist() == rk.tolist() and c.cpu().tolist() == rc.tolist()
     assert np.abs(s.cpu().numpy() - rs).max() < 1e-3
+
+
+@pytest.mark.parametrize("name", ["coca_tiny", "coca_small"])
+def test_absorbed_cross_attention_agrees_with_kv_cache_path(device, name):
+    """Decoder cross-attention in the absorbed-projection form (streams the normalised image tokens, csrc/
+    cross_absorbed.cu) vs the per-layer K/V-cache form of round 1: same teacher-forced logits up to bf16 rounding of
+    the intermediate q' / context tensors, both within the oracle tolerance."""
+    cfg = get_config(name)
+    sd = synth.make_state_dict(cfg, seed=99)
+    g = torch.Generator().manual_seed(8)
+    n, t = 37, 9
+    embs = torch.randn((n, cfg.n_image_embs, cfg.embed_dim), generator=g)
+    text = torch.randint(1, cfg.vocab_size - 2, (n, t), generator=g)
+    outs = []
+    for absorbed in (True, False):
+        model = CoCa(cfg, device=device)
+        model._absorbed = absorbed
+        model.load_state_dict(sd)
+        o = model.forward(None, text.to(device), image_latent=torch.zeros(n, cfg.embed_dim), image_embs=embs.to(device),
+                          output_labels=False)["logits"].cpu()
+        ops.check_watchdog(device)
+        outs.append(o)
+    ref = OracleCoCa(cfg, sd).forward_logits(embs, text)
+    rel_ab = ((outs[0] - ref).norm() / ref.norm()).item()
+    rel_kv = ((outs[1] - ref).norm() / ref.norm()).item()
+    rel = ((outs[0] - outs[1]).norm() / outs[1].norm()).item()
+    print(f"{name}: logits rel err vs oracle: absorbed {rel_ab:.2e}, K/V cache {rel_kv:.2e}; absorbed vs K/V {rel:.2e}")
+    assert rel_ab < 3e-2 and rel_kv < 3e-2 and rel < 3e-2
+    assert rel_ab < 2.0 * rel_kv + 1e-3          # the absorbed form must not be a worse approximation of fp32
