@@ -326,6 +326,8 @@ class CoCa(nn.Module):
                           "ec_decode_greedy")
                 logits_all.append(lg)
         tok = tokens.to(torch.int64)
+        if fixed_output_length and not return_logits:      # the engine path: nothing below depends on where rows ended
+            return {"text": self._out(tok), "logits": []}
         # The reference loop stops as soon as every row has emitted EOS/PAD: T = 1 + last column any row was active.
         ended = (tok[:, 1:] == c.eos_token_id) | (tok[:, 1:] == c.pad_token_id)
         first_end = torch.where(ended.any(dim=1), ended.float().argmax(dim=1) + 1,

@@ -47,8 +47,18 @@ def _resolve_pretrained(model_name: str, pretrained: str, cache_dir: Optional[st
                        f"(no network: place the checkpoint under cache_dir={cache_dir!r} or pass a file path).")
 
 
+# open_clip's precision strings (factory.py:189,254-268).  The native path has ONE arithmetic -- bf16 GEMM / attention
+# operands, fp32 accumulation, fp32 residual stream / LayerNorm / softmax -- whatever is asked for; the reference's
+# `torch.cuda.amp.autocast()` around generate (evaluate_finetuned_model.py:42) is likewise a no-op here.  Unknown
+# strings raise instead of being silently accepted.
+PRECISIONS = ("fp32", "fp16", "bf16", "amp", "amp_bf16", "amp_bfloat16", "pure_fp16", "pure_bf16")
+
+
 def create_model(model_name: str, pretrained: Optional[str] = None, precision: str = "fp32",
                  device: Union[str, torch.device] = "cpu", cache_dir: Optional[str] = None, **_ignored):
+    if precision not in PRECISIONS:
+        raise ValueError(f"precision={precision!r}: expected one of {PRECISIONS} (all run the native bf16-operand / "
+                         "fp32-accumulate arithmetic)")
     cfg = get_config(model_name.replace("/", "-"))
     want = torch.device(device)
     cuda = want if want.type == "cuda" else torch.device("cuda", torch.cuda.current_device()

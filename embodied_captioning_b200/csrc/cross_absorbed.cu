@@ -19,37 +19,58 @@
 // One CTA per SM, persistent over crops (crop = blockIdx.x + i * gridDim.x).  X^ lives in HBM in the "packed" layout
 // pack_image_tokens() writes: per crop ceil(n_kv / 32) chunks of 32 rows, each row T bf16 + 16 B of padding (so that
 // ldmatrix on the staged copy is bank-conflict free), rows past n_kv zero.  A chunk is therefore ONE contiguous
-// 32 x (2T + 16)-byte block and arrives through a 3-deep ring of shared-memory stages with a single cp.async.bulk per
+// 32 x (2T + 16)-byte block and arrives through a 4-deep ring of shared-memory stages with a single cp.async.bulk per
 // chunk completing on an mbarrier (measured: one copy per key ROW -- 32 small bulk copies per chunk issued by one warp
 // -- made the copy issue the critical path, 127 us per launch at 1024 crops); the ring runs ahead across crop
-// boundaries.  8 warps: in the score phase each warp contracts its T/8 slice of the feature dimension for all 32 keys
-// (Q' fragments stay in registers for the whole crop) and the 8 partial tiles are summed through shared memory; in the
-// context phase each warp owns T/8 output columns.  Two __syncthreads per chunk.
+// boundaries.  (The kernel reads "32" wherever the chunk size kKC appears in this comment.)
+//
+// Warp-specialised, 21 warps, every role on its own chunk at any moment:
+//   * producer warp: one bulk copy per chunk (and per crop's Q');
+//   * SCORE group, 8 warps: warp w contracts its T/8 slice of the feature dimension for all 32 keys of a chunk (Q'
+//     fragments stay in registers for the whole crop) and stores a partial 16 x 32 tile (double-buffered);
+//   * SOFTMAX group, 4 warps: sums the 8 partial tiles, online softmax, publishes P (bf16), the rescale factors and the
+//     running normaliser in one of two buffers;
+//   * CONTEXT group, 8 warps: warp w owns T/8 output columns, C = corr * C + P X^ with ldmatrix.trans fragments of the
+//     same stage.
+// mbarriers: full / empty per stage (released by the 16 MMA warps), sfull / sempty per partial buffer, pfull / pempty
+// per P buffer, qfull / qempty for Q'.  Measured on B200 at 1024 crops (profiles/r02_xattn.txt): all warps doing both
+// phases in lock-step with two __syncthreads per chunk ran 90 us per launch with 8 warps (latency-bound: issue slots
+// 16 % busy) and 96 us with 16 warps (shared-memory pipe 69 % busy: twice the partial-tile traffic); score + softmax in
+// one group next to a context group 92 us (the context group waited on the score group's serial S -> softmax chain).
 #include "kernels.cuh"
 
 namespace ec {
 
 namespace xa {
 
-constexpr int kKC = 32;          // keys per chunk
-constexpr int kNS = 3;           // ring depth (chunks)
-constexpr int kWarps = 8;
-constexpr int kThreads = kWarps * 32;
-constexpr int kSpLd = 40;        // floats per row of a partial-score tile (32 + 8 pad: conflict-free float2 stores)
-constexpr int kPLd = 40;         // bf16 per row of the probability tile (80 B: conflict-free ldmatrix)
+#ifndef EC_XA_KC
+#define EC_XA_KC 32
+#endif
+constexpr int kKC = EC_XA_KC;    // keys per chunk (16 or 32)
+constexpr int kNS = 96 / kKC;    // ring depth (chunks): the ring holds 96 keys, all but one chunk of it in flight
+constexpr int kKPT = kKC / 8;    // keys per softmax thread
+constexpr int kPrefetch = 0;     // L2 prefetch ahead of the ring: measured WORSE (125 vs 92 us, 667 vs 426 MB of DRAM reads)
+constexpr int kGroupWarps = 8;   // warps of the score group; the context group has as many
+constexpr int kSoftWarps = 4;    // softmax group: 16 rows x 8 threads, 4 keys of the chunk per thread
+constexpr int kThreads = (2 * kGroupWarps + kSoftWarps + 1) * 32;     // + the producer warp
+constexpr int kSpLd = kKC + 8;   // floats per row of a partial-score tile (+ 8 pad: conflict-free float2 stores)
+constexpr int kPLd = kKC + 8;    // bf16 per row of the probability tile (conflict-free ldmatrix)
 
 template <int T> struct Cfg {
   static constexpr int kRowBytes = T * 2 + 16;
   static constexpr int kStageBytes = kKC * kRowBytes;
   static constexpr int kQRowBytes = T * 2;             // Q' rows are staged unpadded (one contiguous copy per crop)
   static constexpr int kQBytes = 16 * kQRowBytes;
-  static constexpr int kSpBytes = kWarps * 16 * kSpLd * 4;
-  static constexpr int kPBytes = 16 * kPLd * 2;
-  static constexpr int kStatBytes = 2 * 16 * 4;       // corr[16], l[16]
-  static constexpr int kBarBytes = 64;                // full[kNS], qfull
+  static constexpr int kSpBufBytes = kGroupWarps * 16 * kSpLd * 4;
+  static constexpr int kSpBytes = 2 * kSpBufBytes;     // double-buffered between the score and the softmax group
+  static constexpr int kPBytes = 2 * 16 * kPLd * 2;    // double-buffered between the softmax and the context group
+  static constexpr int kStatBytes = 2 * 2 * 16 * 4;    // corr[2][16], l[2][16]
+  static constexpr int kBarBytes = 256;               // full/empty[kNS], sfull/sempty[2], pfull/pempty[2], qfull, qempty
+  static_assert((2 * kNS + 10) * 8 <= kBarBytes, "barrier block too small");
   static constexpr int kSmem = kNS * kStageBytes + kQBytes + kSpBytes + kPBytes + kStatBytes + kBarBytes + 128;
   static_assert(kSmem <= 227 * 1024, "shared memory budget exceeded");
-  static_assert(T % (kWarps * 16) == 0, "feature width must split into 16-wide k-steps per warp");
+  static_assert(T % (kGroupWarps * 16) == 0, "feature width must split into 16-wide k-steps per warp");
+  static_assert(kSoftWarps * 32 == 16 * 8 && (kKC == 32 || kKC == 16), "the softmax maps 128 threads onto 16 rows x 8 key groups");
 };
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -57,6 +78,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -104,9 +128,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, bf16* __restrict__ ctx, int n, int heads,
                       int n_kv, const unsigned char* __restrict__ finished, const DecodeState* __restrict__ st) {
   using C = Cfg<T>;
-  constexpr int DPW = T / kWarps;      // feature columns per warp
-  constexpr int KS = DPW / 16;         // k-steps of the score phase
-  constexpr int NT = DPW / 8;          // n-tiles of the context phase
+  constexpr int DPW = T / kGroupWarps;   // feature columns per warp (of the score and of the context group)
+  constexpr int KS = DPW / 16;           // k-steps of the score phase
+  constexpr int NT = DPW / 8;            // n-tiles of the context phase
   constexpr float kLog2e = 1.4426950408889634f;
   pdl_trigger_top();
   pdl_wait();
@@ -117,14 +141,19 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t stage0 = base;
   const uint32_t qs = base + kNS * C::kStageBytes;
-  float* sp = reinterpret_cast<float*>(gen + kNS * C::kStageBytes + C::kQBytes);
-  uint8_t* pb_gen = reinterpret_cast<uint8_t*>(sp) + C::kSpBytes;
+  float* sp = reinterpret_cast<float*>(gen + kNS * C::kStageBytes + C::kQBytes);          // [2][8 warps][16][kSpLd]
+  uint8_t* pb_gen = reinterpret_cast<uint8_t*>(sp) + C::kSpBytes;                          // P[2][16][kPLd] bf16
   const uint32_t pb = qs + C::kQBytes + C::kSpBytes;
-  float* corr_s = reinterpret_cast<float*>(pb_gen + C::kPBytes);
-  float* l_s = corr_s + 16;
+  float* stat = reinterpret_cast<float*>(pb_gen + C::kPBytes);                             // corr[2][16], l[2][16]
   const uint32_t bar0 = pb + C::kPBytes + C::kStatBytes;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  const uint32_t q_bar = bar0 + 8u * kNS;
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kNS + s); };
+  auto sfull_bar = [&](int b) { return bar0 + 8u * (2 * kNS + b); };
+  auto sempty_bar = [&](int b) { return bar0 + 8u * (2 * kNS + 2 + b); };
+  auto pfull_bar = [&](int b) { return bar0 + 8u * (2 * kNS + 4 + b); };
+  auto pempty_bar = [&](int b) { return bar0 + 8u * (2 * kNS + 6 + b); };
+  const uint32_t qfull_bar = bar0 + 8u * (2 * kNS + 8);
+  const uint32_t qempty_bar = bar0 + 8u * (2 * kNS + 9);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, q4 = lane & 3;
@@ -138,8 +167,18 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
 
   // ---- prologue: barriers; Q' rows past `heads` are zeroed once (0 x NaN = NaN; key rows past n_kv are zero in HBM)
   if (tid == 0) {
-    for (int s = 0; s < kNS; ++s) mbar_init(full_bar(s), 1);
-    mbar_init(q_bar, 1);
+    for (int s = 0; s < kNS; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 2 * kGroupWarps);      // every score warp + every context warp
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(sfull_bar(b), kGroupWarps);           // every score warp stored its partial tile
+      mbar_init(sempty_bar(b), 1);                    // the softmax group consumed the partial tiles
+      mbar_init(pfull_bar(b), 1);                     // the softmax group published P / corr / l
+      mbar_init(pempty_bar(b), kGroupWarps);          // every context warp consumed them
+    }
+    mbar_init(qfull_bar, 1);
+    mbar_init(qempty_bar, kGroupWarps);               // every score warp holds its Q' fragments in registers
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
@@ -149,143 +188,204 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic zero-fill before the async-proxy copies
   __syncthreads();
 
-  int cb = next_active((int)blockIdx.x);      // crop being consumed
-  if (cb >= n) return;
-  int pcrop = cb, pchunk = 0;                 // producer cursor (runs ahead, across crop boundaries)
-  int g_issue = 0, g_use = 0;                 // chunks issued / consumed by this CTA
+  const int first = next_active((int)blockIdx.x);
+  if (first >= n) return;
 
-  auto issue_chunk = [&]() {                  // uniform bookkeeping; one thread issues the chunk's single bulk copy
-    if (pcrop >= n) return;
-    const int stage = g_issue % kNS;
-    if (tid == 0) {
-      mbar_expect_tx(full_bar(stage), (uint32_t)C::kStageBytes);
-      bulk_g2s(stage0 + stage * C::kStageBytes,
-               reinterpret_cast<const uint8_t*>(xn) + ((size_t)pcrop * nchunks + pchunk) * C::kStageBytes,
-               (uint32_t)C::kStageBytes, full_bar(stage));
+  // NOTE on the `__threadfence_block()` before every consumer-side mbarrier arrive: ptxas schedules the SYNCS.ARRIVE
+  // above the warp's last LDSM / HMMA instructions otherwise (seen in the SASS), and the stage was then refilled while
+  // it was still being read -- about one corrupted crop in 300 on B200.
+  if (warp == 2 * kGroupWarps + kSoftWarps) {
+    // =============================================================== producer warp: one bulk copy per chunk / per Q'.
+    // The ring holds two chunks in flight (~97 KB per SM, 14 MB on the chip) -- not enough to cover the HBM latency at
+    // full bandwidth -- so the chunks further ahead are pulled into L2 first (cp.async.bulk.prefetch.L2, kPrefetch
+    // chunks ahead of the copy cursor, across crop boundaries): the copies into shared memory then hit L2.
+    int gi = 0;
+    int pf_crop = first, pf_chunk = 0;
+    auto prefetch_next = [&]() {
+      if (pf_crop >= n) return;
+      if (lane == 0)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint8_t*>(xn) +
+                     ((size_t)pf_crop * nchunks + pf_chunk) * C::kStageBytes), "r"((uint32_t)C::kStageBytes) : "memory");
+      if (++pf_chunk == nchunks) { pf_chunk = 0; pf_crop = next_active(pf_crop + (int)gridDim.x); }
+    };
+    if (kPrefetch > 0) for (int i = 0; i < kPrefetch; ++i) prefetch_next();
+    for (int it = 0, cb = first; cb < n; cb = next_active(cb + (int)gridDim.x), ++it) {
+      if (!mbar_wait(qempty_bar, (uint32_t)((it & 1) ^ 1))) return;        // score warps hold the previous Q' in registers
+      if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(qfull_bar, (uint32_t)heads * (uint32_t)C::kQRowBytes);
+        bulk_g2s(qs, qp + (size_t)cb * heads * T, (uint32_t)heads * (uint32_t)C::kQRowBytes, qfull_bar);
+      }
+      for (int c = 0; c < nchunks; ++c, ++gi) {
+        const int stage = gi % kNS;
+        if (kPrefetch > 0) prefetch_next();
+        if (!mbar_wait(empty_bar(stage), (uint32_t)(((gi / kNS) & 1) ^ 1))) return;
+        if (lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // consumers' generic-proxy reads -> async-proxy write
+          mbar_expect_tx(full_bar(stage), (uint32_t)C::kStageBytes);
+          bulk_g2s(stage0 + stage * C::kStageBytes,
+                   reinterpret_cast<const uint8_t*>(xn) + ((size_t)cb * nchunks + c) * C::kStageBytes,
+                   (uint32_t)C::kStageBytes, full_bar(stage));
+        }
+        __syncwarp();
+      }
     }
-    ++g_issue;
-    if (++pchunk == nchunks) { pchunk = 0; pcrop = next_active(pcrop + (int)gridDim.x); }
-  };
-  auto issue_q = [&](int b) {
-    if (b >= n) return;
-    if (tid == 0) {
-      mbar_expect_tx(q_bar, (uint32_t)heads * (uint32_t)C::kQRowBytes);
-      bulk_g2s(qs, qp + (size_t)b * heads * T, (uint32_t)heads * (uint32_t)C::kQRowBytes, q_bar);
+  } else if (warp < kGroupWarps) {
+    // =============================================================== score group: partial S = Q' X^T per warp
+    int gu = 0;
+    for (int it = 0, cb = first; cb < n; cb = next_active(cb + (int)gridDim.x), ++it) {
+      // the crop's absorbed queries: A fragments of Q' (16 x T, this warp's DPW columns) stay in registers
+      if (!mbar_wait(qfull_bar, (uint32_t)(it & 1))) return;
+      uint32_t qa[KS][4];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+        ldsm_x4(qa[ks], qs + (lane & 15) * C::kQRowBytes + (warp * DPW + ks * 16 + (lane >> 4) * 8) * 2);
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qempty_bar);
+
+      for (int c = 0; c < nchunks; ++c, ++gu) {
+        const int stage = gu % kNS, sb = gu & 1;
+        const uint32_t sbase = stage0 + stage * C::kStageBytes;
+        if (!mbar_wait(full_bar(stage), (uint32_t)((gu / kNS) & 1))) return;
+        float s[kKC / 8][4];
+#pragma unroll
+        for (int i = 0; i < kKC / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+          for (int np = 0; np < kKC / 16; ++np) {
+            uint32_t b[4];
+            ldsm_x4(b, sbase + (np * 16 + (lane & 7) + (lane >> 4) * 8) * C::kRowBytes +
+                           (warp * DPW + ks * 16 + ((lane >> 3) & 1) * 8) * 2);
+            mma16816(s[2 * np], qa[ks], b[0], b[1]);
+            mma16816(s[2 * np + 1], qa[ks], b[2], b[3]);
+          }
+        }
+        if (!mbar_wait(sempty_bar(sb), (uint32_t)(((gu >> 1) & 1) ^ 1))) return;    // softmax consumed chunk gu - 2
+        {
+          float* my = sp + (sb * kGroupWarps + warp) * 16 * kSpLd;
+#pragma unroll
+          for (int nt = 0; nt < kKC / 8; ++nt) {
+            *reinterpret_cast<float2*>(my + g * kSpLd + nt * 8 + 2 * q4) = make_float2(s[nt][0], s[nt][1]);
+            *reinterpret_cast<float2*>(my + (g + 8) * kSpLd + nt * 8 + 2 * q4) = make_float2(s[nt][2], s[nt][3]);
+          }
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(sfull_bar(sb));
+          mbar_arrive(empty_bar(stage));
+        }
+      }
     }
-  };
-
-  issue_q(cb);
-  issue_chunk();
-  issue_chunk();
-
-  for (int it = 0; cb < n; ++it) {
-    const int nb = next_active(cb + (int)gridDim.x);
-    // ---- the crop's absorbed queries: A fragments of Q' (16 x T, this warp's DPW columns) stay in registers
-    if (!mbar_wait(q_bar, (uint32_t)(it & 1))) return;
-    uint32_t qa[KS][4];
+  } else if (warp < 2 * kGroupWarps) {
+    // =============================================================== context group: C = corr * C + P X^
+    const int cw = warp - kGroupWarps;
+    int gu = 0;
+    for (int cb = first; cb < n; cb = next_active(cb + (int)gridDim.x)) {
+      float acc[NT][4];
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
-      ldsm_x4(qa[ks], qs + (lane & 15) * C::kQRowBytes + (warp * DPW + ks * 16 + (lane >> 4) * 8) * 2);
-
-    float acc[NT][4];
-#pragma unroll
-    for (int i = 0; i < NT; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-    float m_run = -INFINITY, l_run = 0.f;        // softmax state of row tid >> 4 (replicated over its 16 threads)
-
-    for (int c = 0; c < nchunks; ++c, ++g_use) {
-      const int stage = g_use % kNS;
-      const uint32_t sbase = stage0 + stage * C::kStageBytes;
-      if (!mbar_wait(full_bar(stage), (uint32_t)((g_use / kNS) & 1))) return;
-
-      // ---- score phase: partial S[16 x 32] over this warp's feature columns
-      float s[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-#pragma unroll
-        for (int np = 0; np < 2; ++np) {
-          uint32_t b[4];
-          ldsm_x4(b, sbase + (np * 16 + (lane & 7) + (lane >> 4) * 8) * C::kRowBytes +
-                         (warp * DPW + ks * 16 + ((lane >> 3) & 1) * 8) * 2);
-          mma16816(s[2 * np], qa[ks], b[0], b[1]);
-          mma16816(s[2 * np + 1], qa[ks], b[2], b[3]);
-        }
-      }
-      {
-        float* my = sp + warp * 16 * kSpLd;
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          *reinterpret_cast<float2*>(my + g * kSpLd + nt * 8 + 2 * q4) = make_float2(s[nt][0], s[nt][1]);
-          *reinterpret_cast<float2*>(my + (g + 8) * kSpLd + nt * 8 + 2 * q4) = make_float2(s[nt][2], s[nt][3]);
-        }
-      }
-      __syncthreads();                                   // (A) partials visible; every warp is past context(c-1)
-      issue_chunk();                                     // refills the stage chunk c-1 used
-      if (c == 0) issue_q(nb);                           // every warp holds its Q' fragments: the buffer is free
-
-      // ---- softmax: thread (r, cp) owns keys 2cp, 2cp+1 of row r
-      {
-        const int r = tid >> 4, cp = tid & 15;
-        float2 v = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-          const float2 t = *reinterpret_cast<const float2*>(sp + (w * 16 + r) * kSpLd + 2 * cp);
-          v.x += t.x; v.y += t.y;
-        }
-        const int key0 = c * kKC + 2 * cp;
-        const float s0 = (key0 < n_kv) ? v.x : -INFINITY;
-        const float s1 = (key0 + 1 < n_kv) ? v.y : -INFINITY;
-        float mx = fmaxf(s0, s1);
-#pragma unroll
-        for (int o = 1; o < 16; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        const float m_new = fmaxf(m_run, mx);            // finite: chunk 0 always holds a valid key
-        const float corr = ex2((m_run - m_new) * kLog2e);
-        const uint32_t pp = pack_bf16x2(ex2((s0 - m_new) * kLog2e), ex2((s1 - m_new) * kLog2e));
-        const float2 pr = unpack_bf16x2(pp);             // the normaliser sums the ROUNDED probabilities the MMA uses
-        float sum = pr.x + pr.y;
-#pragma unroll
-        for (int o = 1; o < 16; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        l_run = l_run * corr + sum;
-        m_run = m_new;
-        *reinterpret_cast<uint32_t*>(pb_gen + (r * kPLd + 2 * cp) * 2) = pp;
-        if (cp == 0) { corr_s[r] = corr; l_s[r] = l_run; }
-      }
-      __syncthreads();                                   // (B) P, corr visible
-
-      // ---- context phase: C[16 x DPW] = corr * C + P[16 x 32] X^[32 x DPW]
-      {
-        const float c_lo = corr_s[g], c_hi = corr_s[g + 8];
+      for (int i = 0; i < NT; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+      float i_lo = 0.f, i_hi = 0.f;
+      for (int c = 0; c < nchunks; ++c, ++gu) {
+        const int stage = gu % kNS, buf = gu & 1;
+        const uint32_t sbase = stage0 + stage * C::kStageBytes;
+        if (!mbar_wait(full_bar(stage), (uint32_t)((gu / kNS) & 1))) return;
+        if (!mbar_wait(pfull_bar(buf), (uint32_t)((gu >> 1) & 1))) return;
+        const float c_lo = stat[buf * 16 + g], c_hi = stat[buf * 16 + g + 8];
+        if (c == nchunks - 1) { i_lo = 1.0f / stat[32 + buf * 16 + g]; i_hi = 1.0f / stat[32 + buf * 16 + g + 8]; }
 #pragma unroll
         for (int i = 0; i < NT; ++i) { acc[i][0] *= c_lo; acc[i][1] *= c_lo; acc[i][2] *= c_hi; acc[i][3] *= c_hi; }
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
+        for (int kk = 0; kk < kKC / 16; ++kk) {
           uint32_t pa[4];
-          ldsm_x4(pa, pb + ((lane & 15) * kPLd + kk * 16 + (lane >> 4) * 8) * 2);
+          ldsm_x4(pa, pb + (((buf * 16) + (lane & 15)) * kPLd + kk * 16 + (lane >> 4) * 8) * 2);
 #pragma unroll
           for (int np = 0; np < NT / 2; ++np) {
             uint32_t b[4];
             ldsm_x4_t(b, sbase + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * C::kRowBytes +
-                             (warp * DPW + np * 16 + (lane >> 4) * 8) * 2);
+                             (cw * DPW + np * 16 + (lane >> 4) * 8) * 2);
             mma16816(acc[2 * np], pa, b[0], b[1]);
             mma16816(acc[2 * np + 1], pa, b[2], b[3]);
           }
         }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) {                                    // this warp's reads of the stage and of P[buf] are done
+          mbar_arrive(empty_bar(stage));
+          mbar_arrive(pempty_bar(buf));
+        }
       }
-    }
-
-    // ---- normalise and store the crop's context rows (heads x T)
-    {
-      const float i_lo = 1.0f / l_s[g], i_hi = 1.0f / l_s[g + 8];
-      bf16* o_lo = ctx + ((size_t)cb * heads + g) * T + warp * DPW + 2 * q4;
-      bf16* o_hi = ctx + ((size_t)cb * heads + g + 8) * T + warp * DPW + 2 * q4;
+      // ---- normalise and store the crop's context rows (heads x T)
+      bf16* o_lo = ctx + ((size_t)cb * heads + g) * T + cw * DPW + 2 * q4;
+      bf16* o_hi = ctx + ((size_t)cb * heads + g + 8) * T + cw * DPW + 2 * q4;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         if (g < heads) *reinterpret_cast<uint32_t*>(o_lo + nt * 8) = pack_bf16x2(acc[nt][0] * i_lo, acc[nt][1] * i_lo);
         if (g + 8 < heads) *reinterpret_cast<uint32_t*>(o_hi + nt * 8) = pack_bf16x2(acc[nt][2] * i_hi, acc[nt][3] * i_hi);
       }
     }
-    cb = nb;
+  } else {
+    // =============================================================== softmax group (128 threads): thread (r, c8) owns
+    // keys 4 c8 .. 4 c8 + 3 of row r; sums the 8 partial tiles, online softmax, publishes P (bf16), corr and l
+    const int t = tid - 2 * kGroupWarps * 32;
+    const int r = t >> 3, c8 = t & 7;
+    int gu = 0;
+    for (int cb = first; cb < n; cb = next_active(cb + (int)gridDim.x)) {
+      float m_run = -INFINITY, l_run = 0.f;      // softmax state of row r (replicated over its 8 threads)
+      for (int c = 0; c < nchunks; ++c, ++gu) {
+        const int buf = gu & 1;
+        if (!mbar_wait(sfull_bar(buf), (uint32_t)((gu >> 1) & 1))) return;
+        float v[kKPT];
+#pragma unroll
+        for (int i = 0; i < kKPT; ++i) v[i] = 0.f;
+        const float* src = sp + (size_t)buf * kGroupWarps * 16 * kSpLd + r * kSpLd + kKPT * c8;
+#pragma unroll
+        for (int w = 0; w < kGroupWarps; ++w) {
+          if constexpr (kKPT == 4) {
+            const float4 x = *reinterpret_cast<const float4*>(src + w * 16 * kSpLd);
+            v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w;
+          } else {
+            const float2 x = *reinterpret_cast<const float2*>(src + w * 16 * kSpLd);
+            v[0] += x.x; v[1] += x.y;
+          }
+        }
+        const int key0 = c * kKC + kKPT * c8;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < kKPT; ++i) { v[i] = (key0 + i < n_kv) ? v[i] : -INFINITY; mx = fmaxf(mx, v[i]); }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float m_new = fmaxf(m_run, mx);            // finite: chunk 0 always holds a valid key
+        const float corr = ex2((m_run - m_new) * kLog2e);
+        uint32_t pk[kKPT / 2];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < kKPT / 2; ++i) {
+          pk[i] = pack_bf16x2(ex2((v[2 * i] - m_new) * kLog2e), ex2((v[2 * i + 1] - m_new) * kLog2e));
+          const float2 a = unpack_bf16x2(pk[i]);         // the normaliser sums the ROUNDED probabilities the MMA uses
+          sum += a.x + a.y;
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        l_run = l_run * corr + sum;
+        m_run = m_new;
+        if (!mbar_wait(pempty_bar(buf), (uint32_t)(((gu >> 1) & 1) ^ 1))) return;   // context group released P[buf]
+        {
+          uint32_t* dst = reinterpret_cast<uint32_t*>(pb_gen + ((buf * 16 + r) * kPLd + kKPT * c8) * 2);
+#pragma unroll
+          for (int i = 0; i < kKPT / 2; ++i) dst[i] = pk[i];
+        }
+        if (c8 == 0) { stat[buf * 16 + r] = corr; stat[32 + buf * 16 + r] = l_run; }
+        __threadfence_block();
+        asm volatile("bar.sync 1, %0;" ::"n"(kSoftWarps * 32) : "memory");     // partials consumed; P, corr, l written
+        if (t == 0) {
+          mbar_arrive(sempty_bar(buf));
+          mbar_arrive(pfull_bar(buf));
+        }
+      }
+    }
   }
   pdl_trigger_bottom();
 }

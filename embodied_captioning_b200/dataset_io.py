@@ -144,7 +144,8 @@ def evaluate_csv(engine, test_csv: str, dest_csv: str, decode: Callable[[np.ndar
             for i in idxs:
                 boxes.append([float(v) for v in ast.literal_eval(rows[i]["bounding_box"])])
                 fidx.append(f); ridx.append(i)
-        out = engine.caption_boxes(frames, np.asarray(boxes, np.float32), fidx, None, POLICY_EVAL, seq_len)
+        # float64: the +-10 px policy and PIL's rounding act on the raw CSV values (transform.box_rects, POLICY_EVAL)
+        out = engine.caption_boxes(frames, np.asarray(boxes, np.float64), fidx, None, POLICY_EVAL, seq_len)
         toks = out["tokens"].cpu().numpy()
         for j, i in enumerate(ridx):
             captions[i] = decode(toks[j])

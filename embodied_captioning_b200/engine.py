@@ -31,10 +31,17 @@ class CaptionEngine:
     # -------------------------------------------------------------------------------------------- device path
     @torch.no_grad()
     def caption_preprocessed(self, x_bf16: torch.Tensor, keys: Optional[torch.Tensor], seq_len: int = 30,
-                             min_seq_len: int = 5, mode: int = ops.MODE_FULL_MEAN_1MINUS) -> Dict[str, torch.Tensor]:
+                             min_seq_len: int = 5, mode: int = ops.MODE_FULL_MEAN_1MINUS,
+                             stage_mark=None) -> Dict[str, torch.Tensor]:
+        """`stage_mark` (optional callable) is invoked after the image tower and after the decoder: bench.py records a
+        CUDA event there to time the stages inside its step loop."""
         latent, embs = self.model._encode_image_dev(x_bf16)
+        if stage_mark is not None:
+            stage_mark()
         gen = self.model.generate(None, image_embs=embs, generation_type="top_k", seq_len=seq_len,
                                   min_seq_len=min_seq_len, fixed_output_length=True, return_logits=False)
+        if stage_mark is not None:
+            stage_mark()
         out = {"tokens": gen["text"], "latent": latent}
         if keys is not None:
             k, s, c = ops.instance_disagreement(latent, keys, mode)

