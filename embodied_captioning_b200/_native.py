@@ -28,7 +28,7 @@ EXPORTS = [
     "ec_caption_frequency_workspace_bytes", "ec_caption_frequency",
     "ec_textenc_create", "ec_textenc_destroy", "ec_textenc_set_tensor", "ec_textenc_finalize",
     "ec_textenc_workspace_bytes", "ec_textenc_encode",
-    "ec_gemm_bf16_grouped", "ec_cross_attention_absorbed", "ec_pack_image_tokens", "ec_packed_image_tokens_bytes",
+    "ec_gemm_bf16_grouped", "ec_gemm_bf16_splitk", "ec_cross_attention_absorbed", "ec_pack_image_tokens", "ec_packed_image_tokens_bytes",
 ]
 
 
@@ -105,11 +105,12 @@ def lib() -> C.CDLL:
     L.ec_textenc_workspace_bytes.argtypes = [vp, i32, i32]
     L.ec_textenc_workspace_bytes.restype = sz
     L.ec_textenc_encode.argtypes = [vp, vp, vp, i32, i32, vp, vp, sz, vp]
+    L.ec_gemm_bf16_splitk.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp, i32, i32, vp, vp, vp]
     L.ec_gemm_bf16_grouped.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp]
     L.ec_packed_image_tokens_bytes.argtypes = [i32, i32, i32]
     L.ec_packed_image_tokens_bytes.restype = sz
     L.ec_pack_image_tokens.argtypes = [vp, vp, i32, i32, i32, i32, vp]
-    L.ec_cross_attention_absorbed.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
+    L.ec_cross_attention_absorbed.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, i32, vp]
     L.ec_launch_count.argtypes = []
     L.ec_launch_count.restype = C.c_int64
     L.ec_profile_gemm.argtypes = [i32]

@@ -262,6 +262,18 @@ int ec_attention_fused_qkv(const void* qkv, int64_t ld, int32_t q_col0, int32_t 
   return attention_full(a, as_stream(stream));
 }
 
+int ec_gemm_bf16_splitk(const void* a, int32_t lda, const void* w, int32_t ldw, int32_t m, int32_t n, int32_t k,
+                        const float* bias, const float* residual, int32_t ldr, float* out, int32_t ldo, int32_t split_k,
+                        float* ws, int32_t* counters, void* stream) {
+  EC_REQUIRE(a && w && residual && out && ws && counters, EC_ERR_INVALID, "ec_gemm_bf16_splitk: null argument");
+  GemmArgs g{};
+  g.A = reinterpret_cast<const bf16*>(a); g.lda = lda; g.W = reinterpret_cast<const bf16*>(w); g.ldw = ldw;
+  g.M = m; g.N = n; g.K = k; g.bias = bias; g.residual = residual; g.ldr = ldr; g.out = out; g.ldo = ldo;
+  g.split_k = split_k > 0 ? split_k : 2;
+  g.sk_ws = ws; g.sk_cnt = counters;
+  return gemm_bf16(g, EPI_F32_RESID, as_stream(stream));
+}
+
 int ec_gemm_bf16_grouped(const void* a, int32_t lda, const void* w, int32_t ldw, int32_t m, int32_t n, int32_t k,
                          int32_t group_cols, const float* bias, void* out, int32_t ldo, int32_t epilogue,
                          int32_t use_simt_reference, void* stream) {
@@ -285,10 +297,10 @@ int ec_pack_image_tokens(const float* x, void* out, int32_t n, int32_t n_kv, int
 }
 
 int ec_cross_attention_absorbed(const void* qp, const void* xn, void* ctx, int32_t batch, int32_t heads, int32_t width,
-                                int32_t n_kv, const uint8_t* finished, void* stream) {
+                                int32_t n_kv, const uint8_t* finished, int32_t reverse, void* stream) {
   EC_REQUIRE(qp && xn && ctx, EC_ERR_INVALID, "ec_cross_attention_absorbed: null argument");
   return decode_cross_absorbed(reinterpret_cast<const bf16*>(qp), reinterpret_cast<const bf16*>(xn),
-                               reinterpret_cast<bf16*>(ctx), batch, heads, width, n_kv, finished, nullptr,
+                               reinterpret_cast<bf16*>(ctx), batch, heads, width, n_kv, finished, nullptr, reverse != 0,
                                as_stream(stream));
 }
 

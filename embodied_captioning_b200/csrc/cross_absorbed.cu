@@ -126,7 +126,7 @@ __device__ __forceinline__ float ex2(float x) {
 template <int T>
 __global__ void __launch_bounds__(kThreads, 1)
 cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, bf16* __restrict__ ctx, int n, int heads,
-                      int n_kv, const unsigned char* __restrict__ finished, const DecodeState* __restrict__ st) {
+                      int n_kv, const unsigned char* __restrict__ finished, const DecodeState* __restrict__ st, int reverse) {
   using C = Cfg<T>;
   constexpr int DPW = T / kGroupWarps;   // feature columns per warp (of the score and of the context group)
   constexpr int KS = DPW / 16;           // k-steps of the score phase
@@ -159,9 +159,13 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
   const int g = lane >> 2, q4 = lane & 3;
   const int nchunks = (n_kv + kKC - 1) / kKC;
 
+  // Traversal order.  The image tokens are the same tensor for every layer, and what the previous layer's launch read
+  // last is still in L2 (126 MB of the 0.4 GB): odd layers walk the crops backwards (`reverse`), so that every launch
+  // starts on the part of the tensor the one before it finished on.  `b` below is a position in the walk.
+  auto crop_of = [&](int b) { return reverse ? n - 1 - b : b; };
   auto next_active = [&](int b) {
     if (finished != nullptr)
-      while (b < n && finished[b]) b += (int)gridDim.x;
+      while (b < n && finished[crop_of(b)]) b += (int)gridDim.x;
     return b;
   };
 
@@ -205,7 +209,7 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
       if (pf_crop >= n) return;
       if (lane == 0)
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint8_t*>(xn) +
-                     ((size_t)pf_crop * nchunks + pf_chunk) * C::kStageBytes), "r"((uint32_t)C::kStageBytes) : "memory");
+                     ((size_t)crop_of(pf_crop) * nchunks + pf_chunk) * C::kStageBytes), "r"((uint32_t)C::kStageBytes) : "memory");
       if (++pf_chunk == nchunks) { pf_chunk = 0; pf_crop = next_active(pf_crop + (int)gridDim.x); }
     };
     if (kPrefetch > 0) for (int i = 0; i < kPrefetch; ++i) prefetch_next();
@@ -214,7 +218,7 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
       if (lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(qfull_bar, (uint32_t)heads * (uint32_t)C::kQRowBytes);
-        bulk_g2s(qs, qp + (size_t)cb * heads * T, (uint32_t)heads * (uint32_t)C::kQRowBytes, qfull_bar);
+        bulk_g2s(qs, qp + (size_t)crop_of(cb) * heads * T, (uint32_t)heads * (uint32_t)C::kQRowBytes, qfull_bar);
       }
       for (int c = 0; c < nchunks; ++c, ++gi) {
         const int stage = gi % kNS;
@@ -224,7 +228,7 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // consumers' generic-proxy reads -> async-proxy write
           mbar_expect_tx(full_bar(stage), (uint32_t)C::kStageBytes);
           bulk_g2s(stage0 + stage * C::kStageBytes,
-                   reinterpret_cast<const uint8_t*>(xn) + ((size_t)cb * nchunks + c) * C::kStageBytes,
+                   reinterpret_cast<const uint8_t*>(xn) + ((size_t)crop_of(cb) * nchunks + c) * C::kStageBytes,
                    (uint32_t)C::kStageBytes, full_bar(stage));
         }
         __syncwarp();
@@ -318,8 +322,8 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
         }
       }
       // ---- normalise and store the crop's context rows (heads x T)
-      bf16* o_lo = ctx + ((size_t)cb * heads + g) * T + cw * DPW + 2 * q4;
-      bf16* o_hi = ctx + ((size_t)cb * heads + g + 8) * T + cw * DPW + 2 * q4;
+      bf16* o_lo = ctx + ((size_t)crop_of(cb) * heads + g) * T + cw * DPW + 2 * q4;
+      bf16* o_hi = ctx + ((size_t)crop_of(cb) * heads + g + 8) * T + cw * DPW + 2 * q4;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         if (g < heads) *reinterpret_cast<uint32_t*>(o_lo + nt * 8) = pack_bf16x2(acc[nt][0] * i_lo, acc[nt][1] * i_lo);
@@ -449,7 +453,7 @@ bool decode_cross_absorbed_supported(int width, int heads, int head_dim, int n_k
 
 template <int T>
 static int launch_xa(const bf16* qp, const bf16* xn, bf16* ctx, int n, int heads, int n_kv, const unsigned char* finished,
-                     const DecodeState* st, cudaStream_t stream) {
+                     const DecodeState* st, int reverse, cudaStream_t stream) {
   using C = xa::Cfg<T>;
   static bool attr_done[64] = {};
   const int dev = current_device();
@@ -461,19 +465,19 @@ static int launch_xa(const bf16* qp, const bf16* xn, bf16* ctx, int n, int heads
   const int grid = std::min(n, num_sms());
   note_launches(1);
   EC_CHECK_CUDA(launch_kernel(xa::cross_absorbed_kernel<T>, dim3(grid), dim3(xa::kThreads), (size_t)C::kSmem, stream, qp, xn,
-                              ctx, n, heads, n_kv, finished, st));
+                              ctx, n, heads, n_kv, finished, st, reverse));
   return EC_OK;
 }
 
 int decode_cross_absorbed(const bf16* qp, const bf16* xn, bf16* ctx, int batch, int heads, int width, int n_kv,
-                          const unsigned char* finished, const DecodeState* st, cudaStream_t stream) {
+                          const unsigned char* finished, const DecodeState* st, bool reverse, cudaStream_t stream) {
   EC_REQUIRE(decode_cross_absorbed_supported(width, heads, width / std::max(heads, 1), n_kv), EC_ERR_UNSUPPORTED,
              "absorbed cross-attention: width %d, heads %d unsupported", width, heads);
   EC_REQUIRE(batch > 0 && qp && xn && ctx, EC_ERR_INVALID, "absorbed cross-attention: bad arguments");
   switch (width) {
-    case 256: return launch_xa<256>(qp, xn, ctx, batch, heads, n_kv, finished, st, stream);
-    case 512: return launch_xa<512>(qp, xn, ctx, batch, heads, n_kv, finished, st, stream);
-    default: return launch_xa<768>(qp, xn, ctx, batch, heads, n_kv, finished, st, stream);
+    case 256: return launch_xa<256>(qp, xn, ctx, batch, heads, n_kv, finished, st, reverse ? 1 : 0, stream);
+    case 512: return launch_xa<512>(qp, xn, ctx, batch, heads, n_kv, finished, st, reverse ? 1 : 0, stream);
+    default: return launch_xa<768>(qp, xn, ctx, batch, heads, n_kv, finished, st, reverse ? 1 : 0, stream);
   }
 }
 

@@ -4,6 +4,7 @@
 // reference loop at coca_model.py:294-327 which syncs on `mask.all()` each step).  Every kernel is launched
 // with programmatic dependent launch so launch latency and CTA scheduling overlap the previous kernel's tail.
 #include "kernels.cuh"
+#include <cstdlib>
 
 namespace ec {
 
@@ -165,14 +166,139 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __res
   if (grp == 0) store_out_slice(out + (size_t)b * C + h * D + sub * 8, acc, inv);
 }
 
+
+// Same computation with EIGHT LANES per (crop, head) instead of a warp: the 12 288 pairs of a 1024-crop step are 3 072
+// warps -- one resident wave on 148 SMs instead of three to five -- and every lane keeps a whole batch of rows in
+// flight.  The warp-per-pair kernel above is latency-bound, not bandwidth-bound: 15.6 us per launch under ncu even at
+// the steps where it moves 8 MB (3 waves x 2 dependent round trips).  Rows 0..kR-1 of the cache are requested at kernel
+// entry, before the step index is known (rows at or past `pos` are masked afterwards: stale but mapped data), together
+// with the control words and the new token's q / k / v; the new token enters the softmax from registers.
+#ifndef EC_SA_R
+#define EC_SA_R 4
+#endif
+#ifndef EC_SA_THREADS
+#define EC_SA_THREADS 128
+#endif
+#ifndef EC_SA_PREFETCH
+#define EC_SA_PREFETCH 0
+#endif
+constexpr int kSaThreads = EC_SA_THREADS;
+constexpr int kSaMinBlocks = (EC_SA_THREADS == 32) ? 21 : 6;
+constexpr int kSaR = EC_SA_R;      // rows per batch and lane group (two batches in flight)
+
+// One-warp CTAs (4 pairs each): 12 288 pairs x 8 lanes = 664 threads per SM at <= 96 registers -- the whole grid is one
+// resident wave (larger CTAs round the per-SM count down and leave a tail).  Batches of kSaR rows, the next batch is
+// requested before the current one is reduced.  Measured in the 1024-crop decode (profiles/r02_decoder_experiments.txt):
+// warp-per-pair 90.3 ms; eight lanes per pair with batches of 8 / 6 / 4 rows and no explicit prefetch 91.6 / 89.5 / 86.9.
+__global__ void __launch_bounds__(kSaThreads, kSaMinBlocks) decode_self_attn_g8_kernel(const bf16* __restrict__ qkv, bf16* kcache, bf16* vcache,
+                                                                     bf16* __restrict__ out, int batch, int heads,
+                                                                     int max_len, const unsigned char* __restrict__ finished,
+                                                                     const DecodeState* __restrict__ st) {
+  constexpr int D = 64;
+  pdl_trigger_top();
+  pdl_wait();
+  const int n_pairs = batch * heads;
+  const int pair_raw = (int)((blockIdx.x * (unsigned)kSaThreads + threadIdx.x) >> 3);
+  const bool valid = pair_raw < n_pairs;
+  const int pair = valid ? pair_raw : n_pairs - 1;          // out-of-range groups shadow the last pair (no stores)
+  const int b = pair / heads, h = pair % heads;
+  const int C = heads * D;
+  const int sub = threadIdx.x & 7;
+  const bf16* row = qkv + (size_t)b * 3 * C + h * D + sub * 8;
+  bf16* kc = kcache + ((size_t)b * max_len) * C + h * D + sub * 8;
+  bf16* vc = vcache + ((size_t)b * max_len) * C + h * D + sub * 8;
+  auto load_rows = [&](uint4 (&kk)[kSaR], uint4 (&vv)[kSaR], int j0, int limit) {
+#pragma unroll
+    for (int r = 0; r < kSaR; ++r) {
+      if (j0 + r < limit) {
+        kk[r] = *reinterpret_cast<const uint4*>(kc + (size_t)(j0 + r) * C);
+        vv[r] = *reinterpret_cast<const uint4*>(vc + (size_t)(j0 + r) * C);
+      }
+    }
+  };
+  uint4 ku[kSaR], vu[kSaR], kn[kSaR], vn[kSaR];
+#pragma unroll
+  for (int r = 0; r < kSaR; ++r) { ku[r] = make_uint4(0, 0, 0, 0); vu[r] = ku[r]; kn[r] = ku[r]; vn[r] = ku[r]; }
+  load_rows(ku, vu, 0, max_len);                             // speculative: before the step index is known
+  const int done = st->done, cur_len = st->cur_len;
+  const unsigned char fin = finished[b];
+  const uint4 knew = *reinterpret_cast<const uint4*>(row + C), vnew = *reinterpret_cast<const uint4*>(row + 2 * C);
+  float qf[8];
+  load_q_slice(row, qf);
+  if (done) return;                                          // warp-uniform
+  const bool live = valid && !fin;                           // per lane group; shuffles below stay warp-wide
+  const int pos = cur_len - 1;
+  if (EC_SA_PREFETCH) load_rows(kn, vn, kSaR, pos);          // second batch, now that the length is known
+  if (live) {
+    *reinterpret_cast<uint4*>(kc + (size_t)pos * C) = knew;
+    *reinterpret_cast<uint4*>(vc + (size_t)pos * C) = vnew;
+  }
+  auto dot8 = [&](const uint4& u) {
+    const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+    float d = a0.x * qf[0] + a0.y * qf[1] + a1.x * qf[2] + a1.y * qf[3] + a2.x * qf[4] + a2.y * qf[5] + a3.x * qf[6] +
+              a3.y * qf[7];
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 4);
+    return d;
+  };
+  float acc[8];
+  float m = dot8(knew), l = 1.f;                             // the new token itself: p = 1 at the running maximum
+  {
+    const float2 a0 = unpack_bf16x2(vnew.x), a1 = unpack_bf16x2(vnew.y), a2 = unpack_bf16x2(vnew.z), a3 = unpack_bf16x2(vnew.w);
+    acc[0] = a0.x; acc[1] = a0.y; acc[2] = a1.x; acc[3] = a1.y; acc[4] = a2.x; acc[5] = a2.y; acc[6] = a3.x; acc[7] = a3.y;
+  }
+  for (int j0 = 0; j0 < pos; j0 += kSaR) {
+    float sc[kSaR];
+    float bm = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < kSaR; ++r) {
+      const float d = dot8(ku[r]);
+      sc[r] = (j0 + r < pos) ? d : -INFINITY;
+      bm = fmaxf(bm, sc[r]);
+    }
+    const float mn = fmaxf(m, bm);                           // m is finite from the start
+    const float corr = __expf(m - mn);
+    m = mn;
+    l *= corr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= corr;
+#pragma unroll
+    for (int r = 0; r < kSaR; ++r) {
+      if (j0 + r < pos) {                                    // rows past pos may hold anything (NaN x 0 = NaN): skipped
+        const float p = __expf(sc[r] - mn);
+        l += p;
+        const uint4 u = vu[r];
+        const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+        acc[0] += p * a0.x; acc[1] += p * a0.y; acc[2] += p * a1.x; acc[3] += p * a1.y;
+        acc[4] += p * a2.x; acc[5] += p * a2.y; acc[6] += p * a3.x; acc[7] += p * a3.y;
+      }
+    }
+    if (EC_SA_PREFETCH) {
+#pragma unroll
+      for (int r = 0; r < kSaR; ++r) { ku[r] = kn[r]; vu[r] = vn[r]; }
+      load_rows(kn, vn, j0 + 2 * kSaR, pos);                 // prefetch the batch after the next
+    } else {
+      load_rows(ku, vu, j0 + kSaR, pos);
+    }
+  }
+  pdl_trigger_bottom();
+  if (live) store_out_slice(out + (size_t)b * C + h * D + sub * 8, acc, 1.0f / l);
+}
+
 int decode_self_attention(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, int batch, int heads, int head_dim,
                           int max_len, const unsigned char* finished, const DecodeState* st, cudaStream_t stream) {
   EC_REQUIRE(max_len <= kMaxKeys, EC_ERR_UNSUPPORTED, "decode: context %d > %d", max_len, kMaxKeys);
   EC_REQUIRE(head_dim == 64, EC_ERR_UNSUPPORTED, "decode self-attention: head_dim %d != 64", head_dim);
-  const int grid = ceil_div(batch * heads, 4);
+  static const int version = [] { const char* e = getenv("EC_SELFATTN"); return e ? atoi(e) : 3; }();
   note_launches(1);
-  EC_CHECK_CUDA(launch_kernel(decode_self_attn_kernel, dim3(grid), dim3(128), 0, stream, qkv, kcache, vcache, out, batch,
-                              heads, max_len, finished, st));
+  if (version == 1) {
+    EC_CHECK_CUDA(launch_kernel(decode_self_attn_kernel, dim3(ceil_div(batch * heads, 4)), dim3(128), 0, stream, qkv, kcache,
+                                vcache, out, batch, heads, max_len, finished, st));
+  } else {
+    EC_CHECK_CUDA(launch_kernel(decode_self_attn_g8_kernel, dim3(ceil_div(batch * heads, kSaThreads / 8)), dim3(kSaThreads),
+                                0, stream, qkv, kcache, vcache, out, batch, heads, max_len, finished, st));
+  }
   return EC_OK;
 }
 

@@ -65,6 +65,18 @@ int gemm_argmax_parts(int N) { return ceil_div(N, 256) * 2; }
 
 static bool pair_shape(int M, int N) { return ceil_div(M, 2 * kBM) * ceil_div(N, 256) >= num_sms() / 2; }
 
+int gemm_choose_split_k(int M, int N, int K) {
+  // Measured on B200 inside the decoder step (profiles/r02_decoder_experiments.txt): correct and bit-reproducible, but
+  // SLOWER for the decoder's FC2 (decode 90.4 -> 96.4 ms at 1024 crops): slice 0 sits behind the other slices'
+  // epilogues, then re-reads their partial tiles, and 144 CTAs poll / fence through L2.  Opt-in (EC_SPLITK=1).
+  static const int mode = [] { const char* e = getenv("EC_SPLITK"); return e ? atoi(e) : 0; }();
+  if (mode == 0 || K < 2048 || K % kBK != 0 || pair_shape(M, N)) return 0;
+  const int tiles = ceil_div(M, kBM) * ceil_div(N, 128), kb = K / kBK;
+  for (int s = 4; s >= 2; --s)
+    if (kb % s == 0 && kb / s >= 2 && tiles * s <= num_sms()) return s;
+  return 0;
+}
+
 bool gemm_uses_pair_kernel(int M, int N) {
   static const int mode = [] { const char* e = getenv("EC_GEMM_PAIR"); return e ? atoi(e) : 1; }();
   return mode != 0 && pair_shape(M, N);
@@ -86,8 +98,11 @@ static int launch_tile(const GemmArgs& a, cudaStream_t stream) {
   p.ln_tiles_n = ceil_div(a.N, BN);
   p.pf_ptr = reinterpret_cast<const unsigned char*>(a.prefetch_ptr); p.pf_bytes = a.prefetch_bytes;
   p.grp_cols = a.group_cols;
+  const int S = (EPI == EPI_F32_RESID && a.split_k > 1) ? a.split_k : 1;
+  p.split_k = S; p.sk_ws = a.sk_ws; p.sk_cnt = a.sk_cnt;
   const int tiles_m = ceil_div(a.M, kBM), tiles_n = ceil_div(a.N, BN);
-  const int grid = std::min(tiles_m * tiles_n, num_sms());
+  EC_REQUIRE(S == 1 || tiles_m * tiles_n * S <= num_sms(), EC_ERR_UNSUPPORTED, "split-K needs one tile slice per SM");
+  const int grid = std::min(tiles_m * tiles_n * S, num_sms());
   static bool attr_done[64] = {};   // per template instantiation and device
   const int dev_ = current_device();
   EC_REQUIRE(dev_ >= 0, EC_ERR_DEVICE, "no current CUDA device");
@@ -117,7 +132,7 @@ static int launch_pair_ew(const GemmArgs& a, cudaStream_t stream) {
   p.skip_flag = a.skip_flag;
   p.ln_g = a.ln_gamma; p.ln_b = a.ln_beta; p.ln_out = a.ln_out; p.ld_ln = a.ld_ln; p.ln_cnt = a.ln_counters;
   p.ln_tiles_n = ceil_div(a.N, BN);
-  p.pf_ptr = nullptr; p.pf_bytes = 0; p.grp_cols = 0;
+  p.pf_ptr = nullptr; p.pf_bytes = 0; p.grp_cols = 0; p.split_k = 1; p.sk_ws = nullptr; p.sk_cnt = nullptr;
   const int tiles_m = ceil_div(a.M, 2 * kBM), tiles_n = ceil_div(a.N, BN);
   const int clusters = std::min(tiles_m * tiles_n, num_sms() / 2);
   static bool attr_done[64] = {};   // per template instantiation and device
@@ -167,6 +182,9 @@ static int launch_epi(const GemmArgs& a, cudaStream_t stream) {
       set_error("grouped GEMM: unsupported tile width %d", bn);
       return EC_ERR_UNSUPPORTED;
     }
+  }
+  if constexpr (EPI == EPI_F32_RESID) {
+    if (a.split_k > 1) return launch_tile<128, EPI>(a, stream);
   }
   if (use_pair_kernel(a)) return launch_pair<256, EPI>(a, stream);
   if constexpr (EPI == EPI_ARGMAX) {
@@ -266,6 +284,14 @@ static int gemm_dispatch(const GemmArgs& a, GemmEpilogue epi, cudaStream_t strea
     EC_REQUIRE(a.N % 4 == 0 && a.N <= kLnTailMaxVec * 128 && a.ld_ln % 4 == 0, EC_ERR_UNSUPPORTED,
                "fused LayerNorm tail: row width %d unsupported", a.N);
   }
+  if (a.split_k > 1) {
+    EC_REQUIRE(epi == EPI_F32_RESID && a.ln_out == nullptr && a.group_cols == 0, EC_ERR_UNSUPPORTED,
+               "split-K belongs to the plain residual epilogue");
+    EC_REQUIRE(a.sk_ws && a.sk_cnt, EC_ERR_INVALID, "split-K needs a partial workspace and tile counters");
+    EC_REQUIRE(a.K % kBK == 0 && (a.K / kBK) % a.split_k == 0 && a.split_k <= 4, EC_ERR_UNSUPPORTED,
+               "split-K: K %d not divisible into %d slices of whole k-blocks", a.K, a.split_k);
+    EC_REQUIRE((reinterpret_cast<uintptr_t>(a.sk_ws) & 15u) == 0 && a.N % 4 == 0, EC_ERR_INVALID, "split-K workspace alignment");
+  }
   if (a.bias) EC_REQUIRE((reinterpret_cast<uintptr_t>(a.bias) & 15u) == 0, EC_ERR_INVALID, "bias not 16-byte aligned");
   switch (epi) {
     case EPI_BF16: return launch_epi<EPI_BF16>(a, stream);
@@ -317,7 +343,7 @@ int gemm_reference_simt(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream
   p.logits = a.logits; p.ld_logits = a.ld_logits; p.logits_step_stride = a.logits_step_stride; p.part_val = a.part_val; p.part_idx = a.part_idx;
   p.n_parts = a.n_parts; p.eos_col = a.eos_col; p.cur_len = a.cur_len; p.min_len = a.min_len; p.skip_flag = nullptr;
   p.ln_g = nullptr; p.ln_b = nullptr; p.ln_out = nullptr; p.ld_ln = 0; p.ln_cnt = nullptr; p.ln_tiles_n = 0;
-  p.pf_ptr = nullptr; p.pf_bytes = 0; p.grp_cols = a.group_cols;
+  p.pf_ptr = nullptr; p.pf_bytes = 0; p.grp_cols = a.group_cols; p.split_k = 1; p.sk_ws = nullptr; p.sk_cnt = nullptr;
   dim3 grid(ceil_div(a.N, 128), a.M);
   gemm_simt_kernel<<<grid, 128, 0, stream>>>(a.A, a.lda, a.W, a.ldw, a.M, a.N, a.K, p, (int)epi);
   EC_POST_LAUNCH();

@@ -247,16 +247,25 @@ struct EpiParams {
   // would otherwise arrive at HBM latency); issued by warp 2 once it has allocated the tensor memory
   const unsigned char* pf_ptr; unsigned long long pf_bytes;
   int grp_cols;     // grouped GEMM: output columns per group (0 = plain GEMM); see GemmArgs::group_cols
+  // Deterministic split-K (EPI_F32_RESID, one tile per CTA): the K range of every output tile is cut into `split_k`
+  // slices run by adjacent CTAs.  Slices 1.. store their raw fp32 accumulators in sk_ws[slice - 1][M][N] and count
+  // themselves on sk_cnt[tile]; slice 0 waits for them and adds them IN SLICE ORDER in its residual epilogue.
+  int split_k; float* sk_ws; int* sk_cnt;
 };
+
+__device__ __forceinline__ float4 ld_cg_f4(const float* p);
 
 // One 32 x 32 chunk.  kFull = the whole chunk lies inside [M, N]: no per-element bound predicates (the interior
 // of the matrix, i.e. nearly every chunk; they were a third of the epilogue's instructions).
 template <int BN, int EPI, bool kFull>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, uint32_t taddr, int row0, int gcol0, int lane,
                                                uint32_t stg, int cur_len, float& best_v, int& best_i,
-                                               uint32_t acc2_off = 0) {
+                                               uint32_t acc2_off = 0, int sk_slice = 0) {
   const int cc = lane & 7;
   const int gcol = gcol0 + cc * 4;
+  // split-K: slice > 0 stores raw accumulators (no bias, no residual); slice 0 adds the other slices' partials
+  const bool sk_raw = (EPI == EPI_F32_RESID) && sk_slice > 0;
+  const int sk_parts = (EPI == EPI_F32_RESID && sk_slice == 0 && p.split_k > 1) ? p.split_k - 1 : 0;
   // The residual may alias the output (in-place residual stream): every element is read and written by the same
   // thread.  All eight loads of the chunk are issued before the TMEM load and the transpose so that their latency
   // is hidden (prefetching a whole chunk further ahead measured no better: 822 vs 842 TFLOP/s on out_proj).
@@ -265,9 +274,20 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, uint32_t tadd
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int grow = row0 + it * 4 + (lane >> 3);
-      rsd[it] = (kFull || (grow < p.M && gcol < p.N))
+      rsd[it] = (!sk_raw && (kFull || (grow < p.M && gcol < p.N)))
                     ? *reinterpret_cast<const float4*>(p.residual + (size_t)grow * p.ldr + gcol)
                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int s = 0; s < sk_parts; ++s) {                 // fixed order: bit-reproducible
+      const float* part = p.sk_ws + (size_t)s * p.M * p.N;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int grow = row0 + it * 4 + (lane >> 3);
+        if (kFull || (grow < p.M && gcol < p.N)) {
+          const float4 t = ld_cg_f4(part + (size_t)grow * p.N + gcol);
+          rsd[it].x += t.x; rsd[it].y += t.y; rsd[it].z += t.z; rsd[it].w += t.w;
+        }
+      }
     }
   }
   uint32_t r[32];
@@ -282,7 +302,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, uint32_t tadd
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
   }
-  if (p.bias != nullptr) {
+  if (p.bias != nullptr && !sk_raw) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       if (kFull || gcol0 + j < p.N) {
@@ -350,7 +370,10 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, uint32_t tadd
           if (EPI == EPI_F32_RESID) {
             o.x += rsd[it].x; o.y += rsd[it].y; o.z += rsd[it].z; o.w += rsd[it].w;
           }
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)grow * p.ldo + gcol) = o;
+          if (sk_raw)
+            *reinterpret_cast<float4*>(p.sk_ws + (size_t)(sk_slice - 1) * p.M * p.N + (size_t)grow * p.N + gcol) = o;
+          else
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)grow * p.ldo + gcol) = o;
         } else {  // EPI_ARGMAX with logits requested
           float* lbase = p.logits + (p.cur_len != nullptr ? (size_t)(cur_len - 1) * p.logits_step_stride : 0);
           *reinterpret_cast<float4*>(lbase + (size_t)grow * p.ld_logits + gcol) = o;
@@ -366,7 +389,8 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, uint32_t tadd
 // shared-memory transpose -> coalesced global row segments.  `row0` = first global row of the slab.
 template <int BN, int EPI, int PARTS = 2>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_acc, int row0, int n_blk, int quad,
-                                              int half, int lane, uint32_t stg, int cur_len, uint32_t acc2_off = 0) {
+                                              int half, int lane, uint32_t stg, int cur_len, uint32_t acc2_off = 0,
+                                              int sk_slice = 0) {
   static_assert(EPI != EPI_ARGMAX || PARTS == 2, "arg-max partial slots are laid out for two column halves");
   constexpr int kColsPerWarp = BN / PARTS;
   constexpr int kChunks = kColsPerWarp / 32;
@@ -379,9 +403,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
     const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)col_in_tile;
     if (gcol0 >= p.N) continue;           // warp-uniform: nothing of this chunk is inside the matrix
     if (rows_full && gcol0 + 32 <= p.N)
-      epilogue_chunk<BN, EPI, true>(p, taddr, row0, gcol0, lane, stg, cur_len, best_v, best_i, acc2_off);
+      epilogue_chunk<BN, EPI, true>(p, taddr, row0, gcol0, lane, stg, cur_len, best_v, best_i, acc2_off, sk_slice);
     else
-      epilogue_chunk<BN, EPI, false>(p, taddr, row0, gcol0, lane, stg, cur_len, best_v, best_i, acc2_off);
+      epilogue_chunk<BN, EPI, false>(p, taddr, row0, gcol0, lane, stg, cur_len, best_v, best_i, acc2_off, sk_slice);
   }
   if (EPI == EPI_ARGMAX && row0 + lane < p.M) {
     const size_t slot = (size_t)(row0 + lane) * p.n_parts + (size_t)(n_blk * 2 + half);
@@ -550,8 +574,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = tiles_m * tiles_n;
-  const int num_kb = (K + kBK - 1) / kBK;
+  // split-K (host guarantees: EPI_F32_RESID, one tile per CTA, k-blocks divisible by split_k): tile index =
+  // (m_blk * tiles_n + n_blk) * S + slice, so the slices of an output tile run on adjacent CTAs
+  const int S = (EPI == EPI_F32_RESID && p.split_k > 1) ? p.split_k : 1;
+  const int num_tiles = tiles_m * tiles_n * S;
+  const int num_kb = ((K + kBK - 1) / kBK) / S;            // k-blocks per slice
+  const int kb0 = ((int)blockIdx.x % S) * num_kb;          // first k-block of this CTA's slice (S > 1: one tile per CTA)
 
   // ---- prologue.  Warp 0 initialises the barriers and at once issues the loads of the first ring-full of
   // k-blocks: they need the barriers but neither the TMEM allocation nor the CTA-wide sync, and in a 6 us kernel
@@ -572,13 +600,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    const int m_blk = (int)blockIdx.x / tiles_n, n_blk = (int)blockIdx.x % tiles_n;
+    const int m_blk = ((int)blockIdx.x / S) / tiles_n, n_blk = ((int)blockIdx.x / S) % tiles_n;
     const int a_k0 = (p.grp_cols > 0) ? (n_blk * BN / p.grp_cols) * K : 0;     // grouped GEMM: this tile's column slab of A
     for (int g = 0; g < pre; ++g) {               // warp-uniform loop, elected lane issues (see the MMA warp)
       if (ptx::elect_one()) {
         ptx::mbar_expect_tx(full_bar(g), Cfg::kStageBytes);
-        ptx::tma_load_2d(smem_a0 + g * Cfg::kABytes, &tmap_a, a_k0 + g * kBK, m_blk * kBM, full_bar(g));
-        ptx::tma_load_2d(smem_b0 + g * Cfg::kBBytes, &tmap_w, g * kBK, n_blk * BN, full_bar(g));
+        ptx::tma_load_2d(smem_a0 + g * Cfg::kABytes, &tmap_a, a_k0 + (kb0 + g) * kBK, m_blk * kBM, full_bar(g));
+        ptx::tma_load_2d(smem_b0 + g * Cfg::kBBytes, &tmap_w, (kb0 + g) * kBK, n_blk * BN, full_bar(g));
       }
       __syncwarp();
     }
@@ -638,7 +666,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int w = (warp == 0) ? 0 : 1;
       int g = 0;                                  // running k-block index of this CTA over all its tiles
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+        const int m_blk = (tile / S) / tiles_n, n_blk = (tile / S) % tiles_n;
         const int a_k0 = (p.grp_cols > 0) ? (n_blk * BN / p.grp_cols) * K : 0;
         for (int kb = 0; kb < num_kb; ++kb, ++g) {
           if ((g & 1) != w || g < pre) continue;      // the first `pre` k-blocks were issued in the prologue
@@ -649,8 +677,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           if (ptx::elect_one()) {
             ptx::mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            ptx::tma_load_2d(smem_a0 + stage * Cfg::kABytes, &tmap_a, a_k0 + kb * kBK, m_blk * kBM, full_bar(stage));
-            ptx::tma_load_2d(smem_b0 + stage * Cfg::kBBytes, &tmap_w, kb * kBK, n_blk * BN, full_bar(stage));
+            ptx::tma_load_2d(smem_a0 + stage * Cfg::kABytes, &tmap_a, a_k0 + (kb0 + kb) * kBK, m_blk * kBM, full_bar(stage));
+            ptx::tma_load_2d(smem_b0 + stage * Cfg::kBBytes, &tmap_w, (kb0 + kb) * kBK, n_blk * BN, full_bar(stage));
           }
           __syncwarp();
         }
@@ -706,19 +734,42 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // HBM-cold every time (weights and cross K/V stream through L2 between two uses), and the epilogue's bias load
     // sat behind the accumulator wait: one DRAM latency on the critical path of every small GEMM.
     if (p.bias != nullptr && (int)blockIdx.x < num_tiles) {
-      const int c = ((int)blockIdx.x % tiles_n) * BN + half * (BN / 2) + lane * 4;
+      const int c = (((int)blockIdx.x / S) % tiles_n) * BN + half * (BN / 2) + lane * 4;
       if (lane < BN / 8 && c < p.N) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c));
         asm volatile("" ::"f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w));
       }
     }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+      const int m_blk = (tile / S) / tiles_n, n_blk = (tile / S) % tiles_n, slice = tile % S;
       if (!bounded_wait(tfull_bar(acc), acc_phase, 4)) break;
       if (dual && !bounded_wait(tfull_bar(1), 0u, 4)) break;      // second issuer's accumulator (stage 1)
       ptx::tc_fence_after();
+      if (S > 1 && slice == 0) {
+        // the other slices of this tile (adjacent, co-resident CTAs) have stored their partial accumulators
+        volatile int* cnt = p.sk_cnt + tile / S;
+        const int target = (S - 1) * kEpiWarps;
+        const long long t0 = clock64();
+        while (*cnt < target) {
+          if (clock64() - t0 > kWatchdogCycles) { atomicExch(&g_gemm_watchdog, 5); break; }
+        }
+        __threadfence();
+      }
       epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m_blk * kBM + quad * 32, n_blk, quad, half, lane, stg,
-                             cur_len, dual ? (uint32_t)BN : 0u);
+                             cur_len, dual ? (uint32_t)BN : 0u, slice);
+      if (S > 1) {
+        __syncwarp();
+        if (lane == 0) {
+          if (slice > 0) {
+            __threadfence();                                    // partial tile visible before the count
+            atomicAdd(p.sk_cnt + tile / S, 1);
+          } else {
+            // every epilogue warp of slice 0 has passed the wait once the count reaches target + kEpiWarps: re-arm
+            const int old = atomicAdd(p.sk_cnt + tile / S, 1);
+            if (old == (S - 1) * kEpiWarps + kEpiWarps - 1) p.sk_cnt[tile / S] = 0;
+          }
+        }
+      }
       // release the accumulator stage back to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();

@@ -45,7 +45,16 @@ struct GemmArgs {
   // by the absorbed cross-attention of the decoder (per-head projections).  K % 64 == 0; 1-CTA kernel, tile width
   // `bn_hint` (0 = the widest of 256 / 128 / 64 that divides group_cols).
   int group_cols; int bn_hint;
+  // Deterministic split-K for the residual epilogue of small-M GEMMs with a long K (decoder FC2: 48 tiles of 128 x 128
+  // with K = 3072 leave 100 SMs idle while every CTA streams 1.5 MB through its own L2 port): split_k in {2, 3, 4}
+  // slices per output tile on adjacent CTAs, partial accumulators through sk_ws ((split_k - 1) * M * N floats), summed
+  // in slice order by slice 0 (bit-reproducible).  sk_cnt: >= tiles ints, zero before the first launch (re-armed by the
+  // kernel).  Needs tiles(128 x 128) * split_k <= SM count and (K / 64) % split_k == 0; 0 / 1 = off.
+  int split_k; float* sk_ws; int* sk_cnt;
 };
+
+// largest usable split_k (0 = none) for a residual GEMM of this shape
+int gemm_choose_split_k(int M, int N, int K);
 
 // true when gemm_bf16 runs this shape on the CTA-pair kernel (whose fused LayerNorm tail needs no inter-CTA sync)
 bool gemm_uses_pair_kernel(int M, int N);

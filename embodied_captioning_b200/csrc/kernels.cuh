@@ -80,8 +80,9 @@ size_t packed_image_tokens_elems(int n, int n_kv, int width);
 // x f32 [n, n_kv, T] -> packed bf16 (32-row chunks, rows of T + 8 elements, zero padding); normalize: (x - mean) * rstd
 int pack_image_tokens(const float* x, bf16* out, int n, int n_kv, int width, bool normalize, cudaStream_t stream);
 bool decode_cross_absorbed_supported(int width, int heads, int head_dim, int n_kv);
+// reverse: walk the crops from the last to the first (alternate layers start on what the previous launch left in L2)
 int decode_cross_absorbed(const bf16* qp, const bf16* xn, bf16* ctx, int batch, int heads, int width, int n_kv,
-                          const unsigned char* finished, const DecodeState* st, cudaStream_t stream);
+                          const unsigned char* finished, const DecodeState* st, bool reverse, cudaStream_t stream);
 // wk_abs [heads*T, head_dim] = per-head transpose of the K projection rows wk [heads*head_dim, T], times `scale`
 int absorb_k_weights(const bf16* wk, bf16* out, int heads, int head_dim, int width, float scale, cudaStream_t stream);
 int decode_cross_absorbed_check_watchdog(cudaStream_t stream);

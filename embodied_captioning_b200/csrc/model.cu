@@ -66,6 +66,13 @@ Model::Model(const ec_config& c, int dev) : cfg(c), device(dev) {
     ln_counters = nullptr;
     fuse_ln = false;
   }
+  const size_t n_sk = (size_t)kMaxChains * kSkCountersPerChain;
+  if (cudaMalloc(&sk_counters, n_sk * sizeof(int)) == cudaSuccess) {
+    cudaMemset(sk_counters, 0, n_sk * sizeof(int));
+    owned.push_back(sk_counters);
+  } else {
+    sk_counters = nullptr;
+  }
   // Measured on B200 (profiles/r01_fused_ln.txt): the fused tail is bit-exact but SLOWER -- one CTA normalises each
   // 128-row block (latency-bound row loop on the GEMM's critical path) where the stand-alone kernel spreads the rows
   // over every SM at the HBM roofline, and every tile pays two named barriers + a device-scope fence + an atomic.
@@ -295,16 +302,21 @@ struct FusedLn {      // LayerNorm applied to the rows of a residual GEMM's outp
 };
 
 struct Prefetch { const void* ptr = nullptr; size_t bytes = 0; };     // the next GEMM's weights -> L2
+struct SplitK { float* ws = nullptr; int* cnt = nullptr; };            // deterministic split-K scratch (gemm_sm100.cuh)
 
 static int linear(const bf16* A, int lda, const bf16* W, int ldw, const float* bias, int M, int N, int K, void* out,
                   int ldo, GemmEpilogue epi, const float* resid, int ldr, const int* skip, cudaStream_t s,
-                  const FusedLn* ln = nullptr, Prefetch pf = Prefetch()) {
+                  const FusedLn* ln = nullptr, Prefetch pf = Prefetch(), SplitK sk = SplitK()) {
   GemmArgs g{};
   g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.M = M; g.N = N; g.K = K; g.bias = bias;
   g.residual = resid; g.ldr = ldr; g.out = out; g.ldo = ldo; g.skip_flag = skip;
   g.prefetch_ptr = pf.ptr; g.prefetch_bytes = pf.bytes;
   if (ln != nullptr && ln->out != nullptr) {
     g.ln_gamma = ln->g; g.ln_beta = ln->b; g.ln_out = ln->out; g.ld_ln = ln->ld; g.ln_counters = ln->counters;
+  } else if (epi == EPI_F32_RESID && sk.ws != nullptr && sk.cnt != nullptr &&
+             ceil_div(M, 128) * ceil_div(N, 128) <= kSkCountersPerChain) {
+    g.split_k = gemm_choose_split_k(M, N, K);
+    g.sk_ws = sk.ws; g.sk_cnt = sk.cnt;
   }
   return gemm_bf16(g, epi, s);
 }
@@ -444,6 +456,7 @@ struct DecodeWs {
   bf16* qp; bf16* ctx;   // absorbed cross-attention: per-head absorbed queries / contexts [n, heads*T]
   float* part_val; int* part_idx; unsigned char* finished; DecodeState* st; int* tokens_tf;
   int* ln_cnt;           // fused-LayerNorm row-block counters of this chain
+  float* sk_ws; int* sk_cnt;   // split-K partial tiles ([3][n][T] floats) and tile counters of this chain's FC2 GEMMs
   size_t cache_layer;    // elements between the self-K/V caches of consecutive layers (whole batch)
   size_t cross_layer;    // elements between the cross-K/V caches of consecutive layers (whole batch)
   size_t bytes;
@@ -463,6 +476,8 @@ static DecodeWs slice_rows(const Model& m, const DecodeWs& w, int r0, int seq_le
   v.part_val += r * parts; v.part_idx += r * parts; v.finished += r; v.tokens_tf += r * L;
   v.st += chain;
   v.ln_cnt = m.ln_counters + kLnCountersEncoder + chain * kLnCountersPerChain;
+  v.sk_ws += r * 3 * T;
+  v.sk_cnt = m.sk_counters ? m.sk_counters + chain * kSkCountersPerChain : nullptr;
   return v;
 }
 
@@ -493,6 +508,8 @@ static DecodeWs carve_decode(const Model& m, void* ws, int n, int seq_len) {
   w.finished = b.take<unsigned char>((size_t)n);
   w.st = b.take<DecodeState>(kMaxChains);
   w.tokens_tf = b.take<int>((size_t)n * L);
+  w.sk_ws = b.take<float>((size_t)n * 3 * T);
+  w.sk_cnt = m.sk_counters;
   w.ln_cnt = m.ln_counters + kLnCountersEncoder;
   w.cache_layer = (size_t)n * L * T;
   w.cross_layer = (size_t)n * NK * 2 * T;
@@ -526,7 +543,7 @@ int Model::self_block(const Block& b, const DecodeWs& w, bf16* kc, bf16* vc, int
                 prefetch_weights ? Prefetch{b.w_fc2, 4 * TT} : none));
   FusedLn nxt{next_g, next_b, fuse ? w.ln : nullptr, T, w.ln_cnt};
   EC_TRY(linear(w.fc1, 4 * T, b.w_fc2, 4 * T, b.b_fc2, n, T, 4 * T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &nxt,
-                prefetch_weights ? next_pf : none));
+                prefetch_weights ? next_pf : none, SplitK{w.sk_ws, w.sk_cnt}));
   return EC_OK;
 }
 
@@ -549,7 +566,8 @@ int Model::cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int la
     gq.A = w.q; gq.lda = T; gq.W = wk_abs[layer]; gq.ldw = hd; gq.M = n; gq.N = H * T; gq.K = hd;
     gq.out = w.qp; gq.ldo = H * T; gq.skip_flag = skip; gq.group_cols = T;
     EC_TRY(gemm_bf16(gq, EPI_BF16, s));
-    EC_TRY(decode_cross_absorbed(w.qp, w.ln_kv, w.ctx, n, H, T, NK, w.finished, w.st, s));
+    static const int env_rev = [] { const char* e = getenv("EC_XA_REVERSE"); return e ? atoi(e) : 1; }();
+    EC_TRY(decode_cross_absorbed(w.qp, w.ln_kv, w.ctx, n, H, T, NK, w.finished, w.st, env_rev != 0 && (layer & 1), s));
     GemmArgs gv{};
     gv.A = w.ctx; gv.lda = H * T; gv.W = wkv_fold[layer] + (size_t)T * T; gv.ldw = T; gv.M = n; gv.N = T; gv.K = T;
     gv.bias = bkv_fold[layer] + T; gv.out = w.att; gv.ldo = T; gv.skip_flag = skip; gv.group_cols = hd; gv.bn_hint = 64;
@@ -565,7 +583,7 @@ int Model::cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int la
                 prefetch_weights ? Prefetch{b.w_fc2, 4 * TT} : none));
   FusedLn nxt{next_g, next_b, fuse ? w.ln : nullptr, T, w.ln_cnt};
   EC_TRY(linear(w.fc1, 4 * T, b.w_fc2, 4 * T, b.b_fc2, n, T, 4 * T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &nxt,
-                prefetch_weights ? next_pf : none));
+                prefetch_weights ? next_pf : none, SplitK{w.sk_ws, w.sk_cnt}));
   return EC_OK;
 }
 

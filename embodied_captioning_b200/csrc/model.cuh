@@ -22,6 +22,7 @@ struct GraphKey { const void* ws; const void* tokens; const void* logits; int n,
 constexpr int kMaxChains = 8;
 constexpr int kLnCountersEncoder = 4096;     // 128-row blocks of one image-tower call (1024 crops x 257 tokens = 2056)
 constexpr int kLnCountersPerChain = 64;      // 128-row blocks of one decoder chain
+constexpr int kSkCountersPerChain = 256;     // output tiles of one split-K GEMM of a decoder chain
 
 struct Model {
   ec_config cfg;
@@ -44,6 +45,7 @@ struct Model {
   bool use_absorbed() const;
   float *unit_gamma = nullptr, *zero_beta = nullptr;
   int* ln_counters = nullptr;      // row-block arrival counters of the fused tails (zero between launches)
+  int* sk_counters = nullptr;      // split-K tile counters of the decoder's FC2 GEMMs, kSkCountersPerChain per chain
   bool use_tc_attention = false;   // tcgen05/TMEM attention for the ViT blocks (option "tc_attention")
   int patch_k = 0, patch_ld = 0;
 

@@ -44,6 +44,24 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     return out
 
 
+def gemm_splitk(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], residual: torch.Tensor, split_k: int = 0,
+                counters: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] f32 = residual + a @ w^T (+ bias) with deterministic split-K (2..4 slices per tile; 0 = choose)."""
+    _check_dev(a, w, bias, residual)
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    ws = torch.empty((3 * M * N,), device=a.device, dtype=torch.float32)
+    if counters is None:
+        counters = torch.zeros(((M + 127) // 128 * ((N + 127) // 128),), device=a.device, dtype=torch.int32)
+    with torch.cuda.device(a.device):
+        nat.check(nat.lib().ec_gemm_bf16_splitk(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K,
+                                                nat.ptr(bias), residual.data_ptr(), residual.stride(0), out.data_ptr(),
+                                                out.stride(0), split_k, ws.data_ptr(), counters.data_ptr(), _stream(a)),
+                  "ec_gemm_bf16_splitk")
+    return out
+
+
 def gemm_grouped(a: torch.Tensor, w: torch.Tensor, group_cols: int, bias: Optional[torch.Tensor] = None,
                  epilogue: int = EPI_BF16, simt_reference: bool = False) -> torch.Tensor:
     """out[m, n] = sum_k a[m, (n // group_cols) * K + k] * w[n, k] (+ bias): a [M, groups*K], w [N, K] bf16."""
@@ -74,7 +92,8 @@ def pack_image_tokens(x: torch.Tensor, normalize: bool = False) -> torch.Tensor:
 
 
 def cross_attention_absorbed(qp: torch.Tensor, xn_packed: torch.Tensor, n_kv: int,
-                             finished: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                             finished: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                             reverse: bool = False) -> torch.Tensor:
     """qp bf16 [B, H, T], xn_packed = pack_image_tokens(...) -> ctx bf16 [B, H, T]: softmax(qp xn^T) xn per crop."""
     _check_dev(qp, xn_packed, finished)
     assert qp.dtype == torch.bfloat16 and xn_packed.dtype == torch.bfloat16 and qp.is_contiguous()
@@ -83,7 +102,7 @@ def cross_attention_absorbed(qp: torch.Tensor, xn_packed: torch.Tensor, n_kv: in
     ctx = torch.zeros_like(qp) if out is None else out
     with torch.cuda.device(qp.device):
         nat.check(nat.lib().ec_cross_attention_absorbed(qp.data_ptr(), xn_packed.data_ptr(), ctx.data_ptr(), B, H, T,
-                                                        n_kv, nat.ptr(finished), _stream(qp)),
+                                                        n_kv, nat.ptr(finished), int(reverse), _stream(qp)),
                   "ec_cross_attention_absorbed")
     return ctx
 

@@ -171,6 +171,14 @@ int ec_attention(const void* q_dev, int64_t q_bs, int64_t q_rs, const void* k_de
 int ec_attention_fused_qkv(const void* qkv_dev, int64_t ld, int32_t q_col0, int32_t k_col0, int32_t v_col0,
                            void* out_dev, int64_t o_bs, int64_t o_rs, int32_t batch, int32_t heads, int32_t seq,
                            int32_t head_dim, int32_t impl, void* stream);
+/* residual GEMM (epilogue 3) with deterministic split-K: every 128 x 128 output tile is computed by `split_k` (2..4, 0 =
+ * choose) adjacent CTAs over disjoint K ranges; partial accumulators travel through ws_dev ((split_k - 1) * m * n
+ * floats) and are added in slice order (bit-reproducible).  counters_dev: >= ceil(m/128) * ceil(n/128) int32, zero
+ * before the first call (re-armed by the kernel).  Used by the decoder's c_proj GEMMs (mlp.c_proj of every
+ * ResidualAttentionBlock: M = crops, K = 4 * width).  Needs tiles * split_k <= SM count and (k / 64) % split_k == 0. */
+int ec_gemm_bf16_splitk(const void* a_bf16_dev, int32_t lda, const void* w_bf16_dev, int32_t ldw, int32_t m, int32_t n,
+                        int32_t k, const float* bias_dev, const float* residual_dev, int32_t ldr, float* out_dev,
+                        int32_t ldo, int32_t split_k, float* ws_dev, int32_t* counters_dev, void* stream);
 /* grouped (block-diagonal) GEMM: out[m, n] = sum_k A[m, (n / group_cols) * k_per_group + k] * W[n, k]; epilogue 0 or 2.
  * The decoder's absorbed cross-attention uses it for the per-head projections on either side of
  * ec_cross_attention_absorbed (reference: the k/v in-projections of text_decoder.cross_attn.{l}.attn, an
@@ -189,7 +197,8 @@ int ec_pack_image_tokens(const float* x_dev, void* out_bf16_dev, int32_t n, int3
  * ctx[b, h, :] = sum_j softmax_j(qp[b, h, :] . xn[b, j, :]) xn[b, j, :].  qp, ctx bf16 [batch, heads * width];
  * xn = ec_pack_image_tokens output; width in {256, 512, 768}, heads <= 16; finished (nullable) uint8 [batch] skips rows. */
 int ec_cross_attention_absorbed(const void* qp_dev, const void* xn_dev, void* ctx_dev, int32_t batch, int32_t heads,
-                                int32_t width, int32_t n_kv, const uint8_t* finished_dev, void* stream);
+                                int32_t width, int32_t n_kv, const uint8_t* finished_dev,
+                                int32_t reverse /* walk the crops last to first: same result, other L2 reuse */, void* stream);
 int ec_check_watchdog(void* stream);   /* EC_ERR_TIMEOUT if a tcgen05 / bulk-copy pipeline wait ever timed out */
 
 /* ---- measurement hooks used by bench.py */

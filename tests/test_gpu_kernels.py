@@ -230,6 +230,8 @@ def test_cross_attention_absorbed_skips_finished_rows(device):
     ops.check_watchdog(device)
     live = fin == 0
     assert torch.equal(part[live], full[live])
+    rev = ops.cross_attention_absorbed(qp, packed, n_kv, finished=fin, reverse=True)     # other traversal, same result
+    assert torch.equal(rev, part)
     assert part[~live].abs().max().item() == 0.0          # untouched (the wrapper zero-fills its output)
 
 
@@ -246,3 +248,24 @@ def test_pack_image_tokens_layout_and_normalisation(device, B, n_kv, T):
         assert p[:, :n_kv, T:].abs().max().item() == 0.0
         if rows > n_kv:
             assert p[:, n_kv:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("M,N,K,S", [(1024, 768, 3072, 3), (1024, 768, 3072, 2), (300, 768, 3072, 4), (1000, 512, 2048, 4),
+                                     (77, 256, 4096, 2)])
+def test_gemm_split_k_is_deterministic_and_matches_fp32(device, M, N, K, S):
+    """Residual GEMM with the K range cut into slices on adjacent CTAs (decoder FC2): equals the fp32 reference, is
+    bit-identical from run to run (fixed summation order), and the tile counters re-arm themselves."""
+    a = _rand_bf16((M, K), device, seed=41)
+    w = _rand_bf16((N, K), device, K ** -0.5, seed=42)
+    bias = torch.randn(N, device=device)
+    res = torch.randn(M, N, device=device)
+    ref = a.float() @ w.float().t() + bias + res
+    cnt = torch.zeros((64,), device=device, dtype=torch.int32)
+    outs = [ops.gemm_splitk(a, w, bias, res, split_k=S, counters=cnt) for _ in range(4)]
+    ops.check_watchdog(device)
+    assert int(cnt.abs().max().item()) == 0                       # re-armed
+    assert (outs[0] - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    plain = ops.gemm(a, w, bias, ops.EPI_F32_RESID, residual=res)
+    assert (plain - outs[0]).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
