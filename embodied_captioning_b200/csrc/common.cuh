@@ -68,19 +68,36 @@ __device__ __forceinline__ void pdl_trigger_top() {}
 __device__ __forceinline__ void pdl_trigger_bottom() { pdl_launch_dependents(); }
 #endif
 
-bool pdl_enabled();   // EC_PDL=1 enables (measured inside the step graph: 127.8 ms with, 121.5 ms without -> default off)
+// EC_PDL: 0 = off, 1 = every kernel of the step (measured inside the step graph in round 1: 127.8 ms with, 121.5 ms
+// without), 2 = only the small non-GEMM kernels (LayerNorm, attention, embed / select), whose CTAs can co-reside with
+// the tail of the GEMM before them (a GEMM CTA holds 231 KB of shared memory: two GEMMs can never overlap on an SM).
+int pdl_mode();
+inline bool pdl_enabled() { return pdl_mode() == 1; }
 
 template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                                        cudaStream_t stream, Args... args) {
+static inline cudaError_t launch_kernel_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                            cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// GEMM launches (gemm_host.cu)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                        cudaStream_t stream, Args... args) {
+  return launch_kernel_pdl(pdl_mode() == 1, kernel, grid, block, smem, stream, args...);
+}
+// the small kernels between the GEMMs
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_small_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                              cudaStream_t stream, Args... args) {
+  return launch_kernel_pdl(pdl_mode() >= 1, kernel, grid, block, smem, stream, args...);
 }
 
 // ----------------------------------------------------------------------------- device helpers

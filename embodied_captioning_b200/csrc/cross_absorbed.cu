@@ -464,7 +464,7 @@ static int launch_xa(const bf16* qp, const bf16* xn, bf16* ctx, int n, int heads
   }
   const int grid = std::min(n, num_sms());
   note_launches(1);
-  EC_CHECK_CUDA(launch_kernel(xa::cross_absorbed_kernel<T>, dim3(grid), dim3(xa::kThreads), (size_t)C::kSmem, stream, qp, xn,
+  EC_CHECK_CUDA(launch_small_kernel(xa::cross_absorbed_kernel<T>, dim3(grid), dim3(xa::kThreads), (size_t)C::kSmem, stream, qp, xn,
                               ctx, n, heads, n_kv, finished, st, reverse));
   return EC_OK;
 }

@@ -36,7 +36,7 @@ int decode_embed(const int* tokens, int ld_tokens, const float* tok_emb, const f
   const long long total = (long long)batch * (width / 4);
   const int grid = (int)std::min<long long>(ceil_div<long long>(total, 256), (long long)num_sms() * 8);
   note_launches(1);
-  EC_CHECK_CUDA(launch_kernel(decode_embed_kernel, dim3(grid), dim3(256), 0, stream, tokens, ld_tokens, tok_emb,
+  EC_CHECK_CUDA(launch_small_kernel(decode_embed_kernel, dim3(grid), dim3(256), 0, stream, tokens, ld_tokens, tok_emb,
                               pos_emb, x, batch, width, st));
   return EC_OK;
 }
@@ -183,14 +183,19 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __res
 #define EC_SA_PREFETCH 0
 #endif
 constexpr int kSaThreads = EC_SA_THREADS;
-constexpr int kSaMinBlocks = (EC_SA_THREADS == 32) ? 21 : 6;
+constexpr int kSaMinBlocks = (EC_SA_THREADS == 32) ? 21 : (EC_SA_THREADS == 96 ? 7 : 6);
 constexpr int kSaR = EC_SA_R;      // rows per batch and lane group (two batches in flight)
 
 // One-warp CTAs (4 pairs each): 12 288 pairs x 8 lanes = 664 threads per SM at <= 96 registers -- the whole grid is one
 // resident wave (larger CTAs round the per-SM count down and leave a tail).  Batches of kSaR rows, the next batch is
 // requested before the current one is reduced.  Measured in the 1024-crop decode (profiles/r02_decoder_experiments.txt):
 // warp-per-pair 90.3 ms; eight lanes per pair with batches of 8 / 6 / 4 rows and no explicit prefetch 91.6 / 89.5 / 86.9.
-__global__ void __launch_bounds__(kSaThreads, kSaMinBlocks) decode_self_attn_g8_kernel(const bf16* __restrict__ qkv, bf16* kcache, bf16* vcache,
+#ifdef EC_SA_MAXNREG
+__global__ void __maxnreg__(EC_SA_MAXNREG) decode_self_attn_g8_kernel(
+#else
+__global__ void __launch_bounds__(kSaThreads, kSaMinBlocks) decode_self_attn_g8_kernel(
+#endif
+    const bf16* __restrict__ qkv, bf16* kcache, bf16* vcache,
                                                                      bf16* __restrict__ out, int batch, int heads,
                                                                      int max_len, const unsigned char* __restrict__ finished,
                                                                      const DecodeState* __restrict__ st) {
@@ -293,10 +298,10 @@ int decode_self_attention(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out
   static const int version = [] { const char* e = getenv("EC_SELFATTN"); return e ? atoi(e) : 3; }();
   note_launches(1);
   if (version == 1) {
-    EC_CHECK_CUDA(launch_kernel(decode_self_attn_kernel, dim3(ceil_div(batch * heads, 4)), dim3(128), 0, stream, qkv, kcache,
+    EC_CHECK_CUDA(launch_small_kernel(decode_self_attn_kernel, dim3(ceil_div(batch * heads, 4)), dim3(128), 0, stream, qkv, kcache,
                                 vcache, out, batch, heads, max_len, finished, st));
   } else {
-    EC_CHECK_CUDA(launch_kernel(decode_self_attn_g8_kernel, dim3(ceil_div(batch * heads, kSaThreads / 8)), dim3(kSaThreads),
+    EC_CHECK_CUDA(launch_small_kernel(decode_self_attn_g8_kernel, dim3(ceil_div(batch * heads, kSaThreads / 8)), dim3(kSaThreads),
                                 0, stream, qkv, kcache, vcache, out, batch, heads, max_len, finished, st));
   }
   return EC_OK;
@@ -334,7 +339,7 @@ int decode_cross_attention(const bf16* q, const bf16* kv, bf16* out, int batch, 
   EC_REQUIRE(n_kv <= kMaxKeys, EC_ERR_UNSUPPORTED, "decode cross-attention: %d keys > %d", n_kv, kMaxKeys);
   const int grid = ceil_div(batch * heads, 4);
   note_launches(1);
-  EC_CHECK_CUDA(launch_kernel(decode_cross_attn_kernel, dim3(grid), dim3(128), 0, stream, q, kv, out, batch, heads, n_kv,
+  EC_CHECK_CUDA(launch_small_kernel(decode_cross_attn_kernel, dim3(grid), dim3(128), 0, stream, q, kv, out, batch, heads, n_kv,
                               finished, st));
   return EC_OK;
 }
@@ -382,7 +387,7 @@ int decode_select(const float* part_val, const int* part_idx, int n_parts, int* 
                   unsigned char* finished, int batch, int seq_len, int eos, int pad, DecodeState* st,
                   cudaStream_t stream) {
   note_launches(1);
-  EC_CHECK_CUDA(launch_kernel(decode_select_kernel, dim3(ceil_div(batch, 8)), dim3(256), 0, stream, part_val, part_idx,
+  EC_CHECK_CUDA(launch_small_kernel(decode_select_kernel, dim3(ceil_div(batch, 8)), dim3(256), 0, stream, part_val, part_idx,
                               n_parts, tokens, ld_tokens, finished, batch, seq_len, eos, pad, st));
   return EC_OK;
 }
@@ -400,7 +405,7 @@ __global__ void decode_advance_kernel(DecodeState* st, int teacher_forced, int b
 
 int decode_advance(DecodeState* st, bool teacher_forced, int batch, cudaStream_t stream) {
   note_launches(1);
-  EC_CHECK_CUDA(launch_kernel(decode_advance_kernel, dim3(1), dim3(1), 0, stream, st, teacher_forced ? 1 : 0, batch));
+  EC_CHECK_CUDA(launch_small_kernel(decode_advance_kernel, dim3(1), dim3(1), 0, stream, st, teacher_forced ? 1 : 0, batch));
   return EC_OK;
 }
 

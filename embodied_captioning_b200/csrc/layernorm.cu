@@ -147,10 +147,10 @@ int layernorm(const float* x, long long ldx, const float* gamma, const float* be
   note_launches(1);
   const bool small = rows <= 8192;      // one wave of blocks: latency, not bandwidth, is what counts
   if (y_is_bf16)
-    EC_CHECK_CUDA(launch_kernel(small ? layernorm_small_kernel<true> : layernorm_kernel<true>, dim3(grid), dim3(wpb * 32), 0,
+    EC_CHECK_CUDA(launch_small_kernel(small ? layernorm_small_kernel<true> : layernorm_kernel<true>, dim3(grid), dim3(wpb * 32), 0,
                                 stream, x, ldx, gamma, beta, y, ldy, rows, width, skip_flag));
   else
-    EC_CHECK_CUDA(launch_kernel(small ? layernorm_small_kernel<false> : layernorm_kernel<false>, dim3(grid), dim3(wpb * 32),
+    EC_CHECK_CUDA(launch_small_kernel(small ? layernorm_small_kernel<false> : layernorm_kernel<false>, dim3(grid), dim3(wpb * 32),
                                 0, stream, x, ldx, gamma, beta, y, ldy, rows, width, skip_flag));
   return EC_OK;
 }
