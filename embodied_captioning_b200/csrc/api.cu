@@ -247,11 +247,11 @@ int ec_attention_fused_qkv(const void* qkv, int64_t ld, int32_t q_col0, int32_t 
                            int32_t impl, void* stream) {
   EC_REQUIRE(qkv && out, EC_ERR_INVALID, "ec_attention_fused_qkv: null argument");
   const bf16* base = reinterpret_cast<const bf16*>(qkv);
-  if (impl == 1) {
+  if (impl == 1 || impl == 2) {      // 2: the whole-row tcgen05 kernel also for 257 tokens (A/B against the block-wise one)
     EC_REQUIRE(attention_sm100_supported(seq, head_dim), EC_ERR_UNSUPPORTED,
                "tcgen05 attention supports head_dim 64 and seq <= 258 (got %d, %d)", head_dim, seq);
     return attention_sm100_fused_qkv(base, ld, q_col0, k_col0, v_col0, reinterpret_cast<bf16*>(out), o_bs, o_rs, batch,
-                                     heads, seq, as_stream(stream));
+                                     heads, seq, as_stream(stream), impl == 2);
   }
   AttnArgs a{};
   a.q = base + q_col0; a.k = base + k_col0; a.v = base + v_col0;

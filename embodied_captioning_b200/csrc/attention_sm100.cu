@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <cstdlib>
 
 namespace ec {
 
@@ -496,6 +497,423 @@ done:
   if (warp == 2) { aptx::tc_fence_after(); aptx::tmem_dealloc(tmem_base, kATmemCols); }
 }
 
+
+// ===================================================================================================
+// v2: the 257-token specialisation (ViT-L/14, ViT-B/16 image towers: 1 class token + 256 patches).
+//
+// What bounded v1 (ncu, profiles/r01_ncu_full_final.csv: tensor pipe 18 %, MUFU 27 %, issue 27 %): a 128-query tile
+// needs a 256-column fp32 S buffer, TMEM holds two of them, so each of the two softmax groups runs its tile's chain
+// QK^T -> row max (first read of S) -> exp (second read of S) -> P.V -> O read strictly in series, and the 257th
+// query costs a third, almost empty, tile per (crop, head).  v2 changes the decomposition:
+//   * keys in two blocks of 128 (+ the 257th key as a 16-column MMA), each block's S is read from TMEM ONCE into
+//     registers (128 fp32 per row thread), exponentiated against the block's own row max and written back as P;
+//     the two blocks accumulate into two separate O accumulators that the epilogue combines with the exact
+//     2^(m_b - m) factors -- no rescaling of O in flight, no second pass over S;
+//   * per softmax group TMEM holds S/P (128 columns) + O_a (64) + O_b (64): the S buffer is free as soon as the
+//     block's P.V has been ISSUED (tcgen05.mma executes in issue order), so the next block's / next pair's QK^T is
+//     in flight while the group is still in its epilogue;
+//   * group g always owns query tile g of the pair (queries 128 g .. 128 g + 127): no third tile.  The 257th query is
+//     one row: a spare warp runs it as a 16 x 272 x 64 flash-attention on mma.sync straight from the staged K / V;
+//   * one warp issues every tcgen05.mma (in-order hazards on the aliased TMEM columns need a single issuer).
+// TMEM columns of group g (base 256 g): [0,128) S block / P (bf16, 64 columns; + 8 columns for the 257th key),
+// [128,192) O_a, [192,256) O_b; the 257th key's score column lands in O_b's first 16 columns before O_b is written.
+//
+//   warp 0: TMA producer | warp 1: MMA issuer | warp 2: TMEM allocator | warp 3: 257th query (mma.sync)
+//   | warps 4-7: softmax group 0 | warps 8-11: softmax group 1
+namespace av2 {
+
+constexpr int kSeq = 257;
+constexpr int kThreads = 12 * 32;
+constexpr int kKvBytes = 2 * kAKBytes + 2048;            // K (272 rows) | V (272 rows) | 16-row box holding query 256
+constexpr int kSmemBytes = 2 * kKvBytes + 4 * kAQBytes + 1024 + 1024;
+static_assert(kKvBytes % 1024 == 0 && kAKBytes % 1024 == 0, "SW128 operands need 1024-byte aligned bases");
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
+
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// exp of 32 score columns against the block's row max: P (bf16) -> 16 TMEM columns, running sum in `sum2`
+__device__ __forceinline__ void exp_chunk(const uint32_t (&v)[32], uint64_t sc2, uint64_t nms2, uint64_t& sum2, uint32_t taddr) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float e0, e1;
+    aptx::unpack_f32x2(aptx::fma_f32x2(aptx::pack_f32x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc2, nms2), e0, e1);
+    const float p0 = aptx::ex2(e0), p1 = aptx::ex2(e1);
+    sum2 = aptx::add_f32x2(sum2, aptx::pack_f32x2(p0, p1));
+    pk[j >> 1] = pack_bf16x2(p0, p1);
+  }
+  aptx::tmem_st16(taddr, pk);
+}
+__device__ __forceinline__ float max_chunk(const uint32_t (&v)[32], float mx) {
+  float m0 = mx, m1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    m0 = aptx::max3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+    m1 = aptx::max3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+  }
+  return fmaxf(m0, m1);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attention257_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16, AttnSm100Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto k_smem = [&](int buf) { return base + (uint32_t)buf * kKvBytes; };
+  auto v_smem = [&](int buf) { return base + (uint32_t)buf * kKvBytes + kAKBytes; };
+  auto qt_smem = [&](int buf) { return base + (uint32_t)buf * kKvBytes + 2u * kAKBytes; };
+  auto q_smem = [&](int grp, int buf) { return base + 2u * kKvBytes + (uint32_t)(grp * 2 + buf) * kAQBytes; };
+  const uint32_t bar0 = base + 2u * kKvBytes + 4u * kAQBytes;
+  // barriers (8 B each)
+  auto KV_FULL = [&](int b) { return bar0 + 8u * (uint32_t)b; };
+  auto KV_EMPTY = [&](int b) { return bar0 + 8u * (uint32_t)(2 + b); };
+  auto Q_FULL = [&](int g, int b) { return bar0 + 8u * (uint32_t)(4 + g * 2 + b); };
+  auto Q_EMPTY = [&](int g, int b) { return bar0 + 8u * (uint32_t)(8 + g * 2 + b); };
+  auto S_FULL = [&](int g) { return bar0 + 8u * (uint32_t)(12 + g); };
+  auto P_READY = [&](int g) { return bar0 + 8u * (uint32_t)(14 + g); };
+  auto O_FULL = [&](int g) { return bar0 + 8u * (uint32_t)(16 + g); };
+  auto O_FREE = [&](int g) { return bar0 + 8u * (uint32_t)(18 + g); };
+  const uint32_t tmem_slot = bar0 + 8u * 24u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_pairs = a.batch * a.heads;
+
+  if (warp == 0 && lane == 0) { aptx::prefetch_tmap(&tm128); aptx::prefetch_tmap(&tm16); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      aptx::mbar_init(KV_FULL(i), 1);
+      aptx::mbar_init(KV_EMPTY(i), 3);         // last P.V commit of either group + the 257th-query warp
+      for (int g = 0; g < 2; ++g) {
+        aptx::mbar_init(Q_FULL(g, i), 1);
+        aptx::mbar_init(Q_EMPTY(g, i), 1);     // commit after the tile's last QK^T
+      }
+      aptx::mbar_init(S_FULL(i), 1);
+      aptx::mbar_init(P_READY(i), 128);
+      aptx::mbar_init(O_FULL(i), 1);
+      aptx::mbar_init(O_FREE(i), 128);
+    }
+    aptx::fence_barrier_init();
+  }
+  if (warp == 2) { aptx::tmem_alloc(tmem_slot, kATmemCols); aptx::tmem_relinquish(); }
+  aptx::tc_fence_before();
+  __syncthreads();
+  aptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    uint32_t it = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
+      const int b = pair / a.heads, h = pair % a.heads;
+      const int row0 = b * kSeq;
+      const int buf = it & 1;
+      const uint32_t par_empty = ((it >> 1) & 1) ^ 1u;
+      if (!await(KV_EMPTY(buf), par_empty, 1)) goto done;
+      if (aptx::elect_one()) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the 257th-query warp reads these tiles with ldmatrix
+        aptx::mbar_expect_tx(KV_FULL(buf), (uint32_t)kKvBytes);
+        const int kc = a.k_col0 + h * kAD, vc = a.v_col0 + h * kAD;
+        aptx::tma_load_2d(k_smem(buf), &tm128, kc, row0, KV_FULL(buf));
+        aptx::tma_load_2d(k_smem(buf) + kAQBytes, &tm128, kc, row0 + 128, KV_FULL(buf));
+        aptx::tma_load_2d(k_smem(buf) + 2 * kAQBytes, &tm16, kc, row0 + 256, KV_FULL(buf));
+        aptx::tma_load_2d(v_smem(buf), &tm128, vc, row0, KV_FULL(buf));
+        aptx::tma_load_2d(v_smem(buf) + kAQBytes, &tm128, vc, row0 + 128, KV_FULL(buf));
+        aptx::tma_load_2d(v_smem(buf) + 2 * kAQBytes, &tm16, vc, row0 + 256, KV_FULL(buf));
+        aptx::tma_load_2d(qt_smem(buf), &tm16, a.q_col0 + h * kAD, row0 + 256, KV_FULL(buf));
+      }
+      __syncwarp();
+      for (int g = 0; g < 2; ++g) {
+        if (!await(Q_EMPTY(g, buf), par_empty, 2)) goto done;
+        if (aptx::elect_one()) {
+          aptx::mbar_expect_tx(Q_FULL(g, buf), kAQBytes);
+          aptx::tma_load_2d(q_smem(g, buf), &tm128, a.q_col0 + h * kAD, row0 + g * kATile, Q_FULL(g, buf));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer (every tcgen05.mma of the CTA, in order)
+    const uint32_t id_qk = idesc_qk(128), id_qt = idesc_qk(16), id_pv = idesc_pv();
+    auto issue_qk = [&](uint32_t t_d, uint32_t q_addr, uint32_t k_addr, uint32_t idesc) {
+      const uint64_t qdesc = desc_kmajor(q_addr), kdesc = desc_kmajor(k_addr);
+#pragma unroll
+      for (int k = 0; k < kAD / 16; ++k)
+        aptx::umma_ss(t_d, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc, k > 0 ? 1u : 0u);
+    };
+    auto issue_pv = [&](uint32_t t_d, uint32_t t_p, uint32_t v_addr, int ksteps) {
+      const uint64_t vdesc0 = desc_mnmajor(v_addr);
+      for (int k = 0; k < ksteps; ++k)
+        aptx::umma_ts(t_d, t_p + (uint32_t)(k * 8), vdesc0 + (uint64_t)(k * (2048 >> 4)), id_pv, k > 0 ? 1u : 0u);
+    };
+    uint32_t it = 0, p_cnt[2] = {0u, 0u};
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t par = (it >> 1) & 1;
+      if (it == 0) {
+        if (!await(KV_FULL(0), 0, 3)) goto done;
+        for (int g = 0; g < 2; ++g) {
+          if (!await(Q_FULL(g, 0), 0, 4)) goto done;
+          aptx::tc_fence_after();
+          if (aptx::elect_one()) {
+            issue_qk(tmem_base + (uint32_t)(g * 256), q_smem(g, 0), k_smem(0), id_qk);
+            aptx::umma_commit(S_FULL(g));
+          }
+          __syncwarp();
+        }
+      }
+      // key block 0 consumed -> O_a = P_0 V_0, the 257th key's scores, S_1 = Q K_1^T
+      for (int g = 0; g < 2; ++g) {
+        if (!await(P_READY(g), p_cnt[g] & 1, 5)) goto done;
+        ++p_cnt[g];
+        if (!await(O_FREE(g), (it & 1) ^ 1u, 6)) goto done;      // the previous tile's epilogue has read O_a / O_b
+        aptx::tc_fence_after();
+        const uint32_t tg = tmem_base + (uint32_t)(g * 256);
+        if (aptx::elect_one()) {
+          issue_pv(tg + 128u, tg, v_smem(buf), 8);
+          issue_qk(tg + 192u, q_smem(g, buf), k_smem(buf) + 2 * kAQBytes, id_qt);
+          issue_qk(tg, q_smem(g, buf), k_smem(buf) + kAQBytes, id_qk);
+          aptx::umma_commit(S_FULL(g));
+          aptx::umma_commit(Q_EMPTY(g, buf));
+        }
+        __syncwarp();
+      }
+      // key block 1 (+ the 257th key) consumed -> O_b = P_1 V_1; then the next pair's first QK^T into the freed S buffer
+      const bool has_next = pair + (int)gridDim.x < n_pairs;
+      const int nbuf = buf ^ 1;
+      const uint32_t npar = ((it + 1) >> 1) & 1;
+      for (int g = 0; g < 2; ++g) {
+        if (!await(P_READY(g), p_cnt[g] & 1, 7)) goto done;
+        ++p_cnt[g];
+        aptx::tc_fence_after();
+        const uint32_t tg = tmem_base + (uint32_t)(g * 256);
+        if (aptx::elect_one()) {
+          issue_pv(tg + 192u, tg, v_smem(buf) + kAQBytes, 9);
+          aptx::umma_commit(O_FULL(g));
+          aptx::umma_commit(KV_EMPTY(buf));
+        }
+        __syncwarp();
+        if (has_next) {
+          if (g == 0 && !await(KV_FULL(nbuf), npar, 8)) goto done;
+          if (!await(Q_FULL(g, nbuf), npar, 9)) goto done;
+          aptx::tc_fence_after();
+          if (aptx::elect_one()) {
+            issue_qk(tg, q_smem(g, nbuf), k_smem(nbuf), id_qk);
+            aptx::umma_commit(S_FULL(g));
+          }
+          __syncwarp();
+        }
+      }
+      (void)par;
+    }
+  } else if (warp == 3) {
+    // ============================================================ the 257th query: one row, mma.sync flash attention
+    // over the staged K / V (rows padded to 16: only row 0 of every fragment is real; rows are independent in an MMA)
+    const int g = lane >> 2, q4 = lane & 3;
+    const float sc = a.scale_log2;
+    uint32_t it = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
+      const int b = pair / a.heads, h = pair % a.heads;
+      const int buf = it & 1;
+      if (!await(KV_FULL(buf), (it >> 1) & 1, 10)) goto done;
+      const uint32_t kb = k_smem(buf), vb = v_smem(buf), qb = qt_smem(buf);
+      uint32_t qa[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int row = lane & 15;
+        ldsm_x4(qa[ks], qb + (uint32_t)row * 128u + (uint32_t)(((ks * 2 + (lane >> 4)) ^ (row & 7)) * 16));
+      }
+      float acc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+      float m_run = -INFINITY, l_run = 0.f;
+      // 4 chunks of 64 keys + the 16-key box that holds key 256
+#pragma unroll 1
+      for (int c = 0; c < 5; ++c) {
+        const int k0 = c * 64;
+        const int npairs_n = (c < 4) ? 4 : 1;        // pairs of 8-key n-tiles in this chunk
+        float s[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {
+            if (np < npairs_n) {
+              const int key = k0 + np * 16 + (lane & 7) + (lane >> 4) * 8;
+              uint32_t bf[4];
+              ldsm_x4(bf, kb + (uint32_t)key * 128u + (uint32_t)(((ks * 2 + ((lane >> 3) & 1)) ^ (key & 7)) * 16));
+              mma16816(s[2 * np], qa[ks], bf[0], bf[1]);
+              mma16816(s[2 * np + 1], qa[ks], bf[2], bf[3]);
+            }
+          }
+        }
+        float cm = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          if (nt < 2 * npairs_n) {
+            const int key = k0 + nt * 8 + 2 * q4;
+            if (key >= kSeq) s[nt][0] = -INFINITY;
+            if (key + 1 >= kSeq) s[nt][1] = -INFINITY;
+            cm = fmaxf(cm, fmaxf(s[nt][0], s[nt][1]));
+          }
+        }
+        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
+        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
+        const float m_new = fmaxf(m_run, cm);
+        const float corr = aptx::ex2((m_run - m_new) * sc);
+        const float nms = -m_new * sc;
+        float sum = 0.f;
+        uint32_t pa[4][4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (kk < npairs_n) {
+            const float p00 = aptx::ex2(fmaf(s[2 * kk][0], sc, nms)), p01 = aptx::ex2(fmaf(s[2 * kk][1], sc, nms));
+            const float p10 = aptx::ex2(fmaf(s[2 * kk + 1][0], sc, nms)), p11 = aptx::ex2(fmaf(s[2 * kk + 1][1], sc, nms));
+            sum += (p00 + p01) + (p10 + p11);
+            pa[kk][0] = pack_bf16x2(p00, p01); pa[kk][1] = 0u;       // rows 8..15 of the fragment: zero
+            pa[kk][2] = pack_bf16x2(p10, p11); pa[kk][3] = 0u;
+          }
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        l_run = l_run * corr + sum;
+        m_run = m_new;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc[i][0] *= corr; acc[i][1] *= corr; }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (kk < npairs_n) {
+#pragma unroll
+            for (int dp = 0; dp < 4; ++dp) {
+              const int key = k0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+              uint32_t bf[4];
+              ldsm_x4_t(bf, vb + (uint32_t)key * 128u + (uint32_t)(((dp * 2 + (lane >> 4)) ^ (key & 7)) * 16));
+              mma16816(acc[2 * dp], pa[kk], bf[0], bf[1]);
+              mma16816(acc[2 * dp + 1], pa[kk], bf[2], bf[3]);
+            }
+          }
+        }
+      }
+      __threadfence_block();       // keep the arrive below the last ldmatrix (see cross_absorbed.cu)
+      __syncwarp();
+      if (lane == 0) aptx::mbar_arrive(KV_EMPTY(buf));
+      if (g == 0) {
+        const float inv = 1.0f / l_run;
+        bf16* orow = a.out + (size_t)b * a.o_bs + (size_t)(kSeq - 1) * a.o_rs + (size_t)h * kAD + 2 * q4;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+          *reinterpret_cast<uint32_t*>(orow + nt * 8) = pack_bf16x2(acc[nt][0] * inv, acc[nt][1] * inv);
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================================================ softmax + epilogue: one thread per query row
+    const int grp = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t tg = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * 256);
+    const float sc = a.scale_log2;
+    const uint64_t sc2 = aptx::pack_f32x2(sc, sc);
+    uint32_t it = 0, s_cnt = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
+      const int b = pair / a.heads, h = pair % a.heads;
+      float ms[2], l[2];
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {
+        if (!await(S_FULL(grp), s_cnt & 1, 11)) goto done;
+        ++s_cnt;
+        aptx::tc_fence_after();
+        uint32_t v0[32], v1[32], v2[32], v3[32], vt = 0u;
+        aptx::tmem_ld32(tg, v0);
+        aptx::tmem_ld32(tg + 32u, v1);
+        aptx::tmem_ld32(tg + 64u, v2);
+        aptx::tmem_ld32(tg + 96u, v3);
+        if (blk == 1) tmem_ld1(tg + 192u, vt);
+        aptx::tmem_ld_wait();
+        float mx = (blk == 1) ? __uint_as_float(vt) : -INFINITY;
+        mx = max_chunk(v0, mx);
+        mx = fmaxf(mx, max_chunk(v1, -INFINITY));
+        mx = fmaxf(mx, max_chunk(v2, -INFINITY));
+        mx = fmaxf(mx, max_chunk(v3, -INFINITY));
+        const float m_s = mx * sc;
+        const uint64_t nms2 = aptx::pack_f32x2(-m_s, -m_s);
+        uint64_t sum2 = aptx::pack_f32x2(0.f, 0.f);
+        exp_chunk(v0, sc2, nms2, sum2, tg);
+        exp_chunk(v1, sc2, nms2, sum2, tg + 16u);
+        exp_chunk(v2, sc2, nms2, sum2, tg + 32u);
+        exp_chunk(v3, sc2, nms2, sum2, tg + 48u);
+        float s_lo, s_hi;
+        aptx::unpack_f32x2(sum2, s_lo, s_hi);
+        float sum = s_lo + s_hi;
+        if (blk == 1) {
+          const float pt = aptx::ex2(fmaf(__uint_as_float(vt), sc, -m_s));
+          sum += pt;
+          const uint32_t pk[8] = {pack_bf16x2(pt, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};     // keys 256 | 257..271 (padding)
+          tmem_st8(tg + 64u, pk);
+        }
+        ms[blk] = m_s;
+        l[blk] = sum;
+        aptx::tmem_st_wait();
+        aptx::tc_fence_before();
+        aptx::mbar_arrive(P_READY(grp));
+      }
+      // ---- epilogue: o = (O_a 2^(m_a - m) + O_b 2^(m_b - m)) / (l_a 2^(m_a - m) + l_b 2^(m_b - m))
+      const float m = fmaxf(ms[0], ms[1]);
+      const float a0 = aptx::ex2(ms[0] - m), a1 = aptx::ex2(ms[1] - m);
+      const float inv = 1.0f / fmaf(l[0], a0, l[1] * a1);
+      const float c0 = a0 * inv, c1 = a1 * inv;
+      if (!await(O_FULL(grp), it & 1, 12)) goto done;
+      aptx::tc_fence_after();
+      uint32_t oa[32], ob[32];
+      uint32_t res[32];
+      aptx::tmem_ld32(tg + 128u, oa);
+      aptx::tmem_ld32(tg + 192u, ob);
+      aptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 2)
+        res[j >> 1] = pack_bf16x2(fmaf(__uint_as_float(oa[j]), c0, __uint_as_float(ob[j]) * c1),
+                                  fmaf(__uint_as_float(oa[j + 1]), c0, __uint_as_float(ob[j + 1]) * c1));
+      aptx::tmem_ld32(tg + 160u, oa);
+      aptx::tmem_ld32(tg + 224u, ob);
+      aptx::tmem_ld_wait();
+      aptx::tc_fence_before();
+      aptx::mbar_arrive(O_FREE(grp));                     // both accumulators are in registers
+#pragma unroll
+      for (int j = 0; j < 32; j += 2)
+        res[16 + (j >> 1)] = pack_bf16x2(fmaf(__uint_as_float(oa[j]), c0, __uint_as_float(ob[j]) * c1),
+                                         fmaf(__uint_as_float(oa[j + 1]), c0, __uint_as_float(ob[j + 1]) * c1));
+      bf16* orow = a.out + (size_t)b * a.o_bs + (size_t)(grp * kATile + r) * a.o_rs + (size_t)h * kAD;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(res[4 * c], res[4 * c + 1], res[4 * c + 2], res[4 * c + 3]);
+    }
+  }
+done:
+  aptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { aptx::tc_fence_after(); aptx::tmem_dealloc(tmem_base, kATmemCols); }
+}
+
+}  // namespace av2
+
 // ---------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiledA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -528,7 +946,8 @@ bool attention_sm100_supported(int seq, int head_dim) {
 }
 
 int attention_sm100_fused_qkv(const bf16* qkv, long long ld, int q_col0, int k_col0, int v_col0, bf16* out,
-                              long long o_bs, long long o_rs, int batch, int heads, int seq, cudaStream_t stream) {
+                              long long o_bs, long long o_rs, int batch, int heads, int seq, cudaStream_t stream,
+                              bool force_v1) {
   EC_REQUIRE(attention_sm100_supported(seq, kAD), EC_ERR_UNSUPPORTED, "tcgen05 attention: seq %d unsupported", seq);
   EC_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15u) == 0, EC_ERR_INVALID, "tcgen05 attention: alignment");
   EC_REQUIRE(o_rs % 8 == 0 && o_bs % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0, EC_ERR_INVALID,
@@ -553,6 +972,18 @@ int attention_sm100_fused_qkv(const bf16* qkv, long long ld, int q_col0, int k_c
   a.q_col0 = q_col0; a.k_col0 = k_col0; a.v_col0 = v_col0;
   a.scale_log2 = 0.125f * 1.4426950408889634f;
   const int grid = std::min(batch * heads, num_sms());
+  // 257 tokens (ViT-L/14, ViT-B/16): the block-wise kernel (EC_ATTN_V2=0 or impl 2 of ec_attention_fused_qkv keep v1)
+  static const int env_v2 = [] { const char* e = getenv("EC_ATTN_V2"); return e ? atoi(e) : 1; }();
+  if (seq == av2::kSeq && env_v2 != 0 && !force_v1) {
+    static bool attr2[64] = {};
+    if (!attr2[dev_]) {
+      EC_CHECK_CUDA(cudaFuncSetAttribute(av2::attention257_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av2::kSmemBytes));
+      attr2[dev_] = true;
+    }
+    av2::attention257_kernel<<<grid, av2::kThreads, av2::kSmemBytes, stream>>>(tm128, tm16, a);
+    EC_POST_LAUNCH();
+    return EC_OK;
+  }
   const int n_mma = std::min((seq + 15) & ~15, kAKeysMma);
   if (std::min(seq, kAKeysMma) == n_mma)
     attention_sm100_kernel<false><<<grid, kAThreads, kASmemBytes, stream>>>(tm128, tm16, a);

@@ -47,8 +47,11 @@ int attention_full(const AttnArgs& a, cudaStream_t stream);
 // ---- attention_sm100.cu (ViT blocks: tcgen05.mma with S, P and O in TMEM; q/k/v are column slices of one
 // fused [batch*seq, ld] bf16 buffer; head_dim 64, seq <= 258) ----------------------------------------
 bool attention_sm100_supported(int seq, int head_dim);
+// seq == 257 runs the block-wise kernel (two 128-key blocks per query tile, the 257th query on a spare mma.sync warp);
+// `force_v1` keeps the whole-row kernel for A/B runs
 int attention_sm100_fused_qkv(const bf16* qkv, long long ld, int q_col0, int k_col0, int v_col0, bf16* out,
-                              long long o_bs, long long o_rs, int batch, int heads, int seq, cudaStream_t stream);
+                              long long o_bs, long long o_rs, int batch, int heads, int seq, cudaStream_t stream,
+                              bool force_v1 = false);
 int attention_sm100_check_watchdog(cudaStream_t stream);
 
 // ---- decode.cu (KV-cached greedy decoder, one new token per crop per step) -----------------------

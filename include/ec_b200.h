@@ -167,7 +167,8 @@ int ec_attention(const void* q_dev, int64_t q_bs, int64_t q_rs, const void* k_de
                  const void* v_dev, int64_t v_bs, int64_t v_rs, void* o_dev, int64_t o_bs, int64_t o_rs,
                  int32_t batch, int32_t heads, int32_t sq, int32_t skv, int32_t head_dim, void* stream);
 /* q/k/v as column slices of one fused [batch*seq, ld] bf16 buffer (the layout the image tower uses);
- * impl 0 = mma.sync flash kernel, 1 = tcgen05/TMEM kernel (head_dim 64, seq <= 258) */
+ * impl 0 = mma.sync flash kernel, 1 = tcgen05/TMEM kernels (head_dim 64, seq <= 258; 257 tokens run the block-wise kernel),
+ * 2 = the whole-row tcgen05 kernel for every length (A/B) */
 int ec_attention_fused_qkv(const void* qkv_dev, int64_t ld, int32_t q_col0, int32_t k_col0, int32_t v_col0,
                            void* out_dev, int64_t o_bs, int64_t o_rs, int32_t batch, int32_t heads, int32_t seq,
                            int32_t head_dim, int32_t impl, void* stream);

@@ -131,7 +131,7 @@ def test_attention_strided_fused_qkv_and_shared_queries(device):
 
 
 @pytest.mark.parametrize("B,H,S", [(3, 16, 257), (2, 12, 50), (2, 4, 256), (2, 4, 258), (5, 3, 130), (1, 1, 17),
-                                   (1, 2, 1), (300, 2, 257)])
+                                   (1, 2, 1), (300, 2, 257), (1, 1, 257), (149, 1, 257), (37, 16, 257)])
 def test_attention_tcgen05_fused_qkv(device, B, H, S):
     """ViT-block attention on tcgen05/TMEM (S = QK^T, P and O in tensor memory) vs an fp32 reference and vs the
     mma.sync kernel, on the fused [B, S, 3*H*64] layout of the image tower."""
@@ -140,6 +140,9 @@ def test_attention_tcgen05_fused_qkv(device, B, H, S):
     qkv = _rand_bf16((B, S, 3 * C), device, seed=31)
     out = ops.attention_fused_qkv(qkv, H, impl=1)
     ops.check_watchdog(device)
+    whole_row = ops.attention_fused_qkv(qkv, H, impl=2)     # 257 tokens: impl 1 is the block-wise kernel, 2 the whole-row one
+    ops.check_watchdog(device)
+    assert (out.float() - whole_row.float()).abs().max().item() < 0.03
     legacy = ops.attention_fused_qkv(qkv, H, impl=0)
     qf = qkv[:, :, :C].float().view(B, S, H, D).transpose(1, 2)
     kf = qkv[:, :, C:2 * C].float().view(B, S, H, D).transpose(1, 2)
