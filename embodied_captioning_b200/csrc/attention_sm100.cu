@@ -513,19 +513,19 @@ done:
 //     block's P.V has been ISSUED (tcgen05.mma executes in issue order), so the next block's / next pair's QK^T is
 //     in flight while the group is still in its epilogue;
 //   * group g always owns query tile g of the pair (queries 128 g .. 128 g + 127): no third tile.  The 257th query is
-//     one row: a spare warp runs it as a 16 x 272 x 64 flash-attention on mma.sync straight from the staged K / V;
+//     one row: two spare warps run it on the fp32 pipe straight from the staged K / V;
 //   * one warp issues every tcgen05.mma (in-order hazards on the aliased TMEM columns need a single issuer).
 // TMEM columns of group g (base 256 g): [0,128) S block / P (bf16, 64 columns; + 8 columns for the 257th key),
 // [128,192) O_a, [192,256) O_b; the 257th key's score column lands in O_b's first 16 columns before O_b is written.
 //
-//   warp 0: TMA producer | warp 1: MMA issuer | warp 2: TMEM allocator | warp 3: 257th query (mma.sync)
+//   warp 0: TMA producer | warp 1: MMA issuer | warps 2-3: 257th query (warp 2 also owns the TMEM allocation)
 //   | warps 4-7: softmax group 0 | warps 8-11: softmax group 1
 namespace av2 {
 
 constexpr int kSeq = 257;
 constexpr int kThreads = 12 * 32;
 constexpr int kKvBytes = 2 * kAKBytes + 2048;            // K (272 rows) | V (272 rows) | 16-row box holding query 256
-constexpr int kSmemBytes = 2 * kKvBytes + 4 * kAQBytes + 1024 + 1024;
+constexpr int kSmemBytes = 2 * kKvBytes + 4 * kAQBytes + 3072 + 1024;   // + barriers, 257th-query scratch, alignment
 static_assert(kKvBytes % 1024 == 0 && kAKBytes % 1024 == 0, "SW128 operands need 1024-byte aligned bases");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 
@@ -536,20 +536,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
 // exp of 32 score columns against the block's row max: P (bf16) -> 16 TMEM columns, running sum in `sum2`
 __device__ __forceinline__ void exp_chunk(const uint32_t (&v)[32], uint64_t sc2, uint64_t nms2, uint64_t& sum2, uint32_t taddr) {
   uint32_t pk[16];
@@ -601,7 +587,7 @@ attention257_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       aptx::mbar_init(KV_FULL(i), 1);
-      aptx::mbar_init(KV_EMPTY(i), 3);         // last P.V commit of either group + the 257th-query warp
+      aptx::mbar_init(KV_EMPTY(i), 4);         // last P.V commit of either group + the two 257th-query warps
       for (int g = 0; g < 2; ++g) {
         aptx::mbar_init(Q_FULL(g, i), 1);
         aptx::mbar_init(Q_EMPTY(g, i), 1);     // commit after the tile's last QK^T
@@ -629,7 +615,7 @@ attention257_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_cons
       const uint32_t par_empty = ((it >> 1) & 1) ^ 1u;
       if (!await(KV_EMPTY(buf), par_empty, 1)) goto done;
       if (aptx::elect_one()) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the 257th-query warp reads these tiles with ldmatrix
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the 257th-query warps read these tiles with generic loads
         aptx::mbar_expect_tx(KV_FULL(buf), (uint32_t)kKvBytes);
         const int kc = a.k_col0 + h * kAD, vc = a.v_col0 + h * kAD;
         aptx::tma_load_2d(k_smem(buf), &tm128, kc, row0, KV_FULL(buf));
@@ -724,10 +710,16 @@ attention257_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_cons
       }
       (void)par;
     }
-  } else if (warp == 3) {
-    // ============================================================ the 257th query: one row, mma.sync flash attention
-    // over the staged K / V (rows padded to 16: only row 0 of every fragment is real; rows are independent in an MMA)
-    const int g = lane >> 2, q4 = lane & 3;
+  } else if (warp == 2 || warp == 3) {
+    // ============================================================ the 257th query: one row, on the fp32 pipe of two
+    // spare warps (warp 2: keys 0..127, warp 3: keys 128..256).  Scores: a lane per key (K rows straight from the staged
+    // tile); context: a lane per pair of feature columns, the warp's probabilities broadcast from shared memory; warp 3
+    // merges the two partial softmaxes.  (Measured: the same row as a 16 x 272 x 64 mma.sync flash attention on ONE warp
+    // took 13 k cycles per (crop, head) -- legacy HMMA at ~48 cycles each -- and was the critical path of the CTA.)
+    const int tw = warp - 2;
+    float* tail_f = reinterpret_cast<float*>(smem_raw + (bar0 + 256u - smem_u32(smem_raw)));
+    float* pbuf = tail_f + tw * 132;                 // this warp's probabilities [129]
+    float* part = tail_f + 2 * 132;                  // warp 2's partial (m, l, acc[64]), double-buffered by pair parity
     const float sc = a.scale_log2;
     uint32_t it = 0;
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
@@ -735,93 +727,89 @@ attention257_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_cons
       const int buf = it & 1;
       if (!await(KV_FULL(buf), (it >> 1) & 1, 10)) goto done;
       const uint32_t kb = k_smem(buf), vb = v_smem(buf), qb = qt_smem(buf);
-      uint32_t qa[4][4];
+      float q[kAD];
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const int row = lane & 15;
-        ldsm_x4(qa[ks], qb + (uint32_t)row * 128u + (uint32_t)(((ks * 2 + (lane >> 4)) ^ (row & 7)) * 16));
+      for (int c = 0; c < 8; ++c) {
+        const uint4 u = aptx::ld_shared_u4(qb + (uint32_t)(c * 16));          // row 0 of the box: swizzle term is 0
+        const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+        q[c * 8 + 0] = f0.x; q[c * 8 + 1] = f0.y; q[c * 8 + 2] = f1.x; q[c * 8 + 3] = f1.y;
+        q[c * 8 + 4] = f2.x; q[c * 8 + 5] = f2.y; q[c * 8 + 6] = f3.x; q[c * 8 + 7] = f3.y;
       }
-      float acc[8][4];
+      auto dot_key = [&](int key) {
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-      float m_run = -INFINITY, l_run = 0.f;
-      // 4 chunks of 64 keys + the 16-key box that holds key 256
-#pragma unroll 1
-      for (int c = 0; c < 5; ++c) {
-        const int k0 = c * 64;
-        const int npairs_n = (c < 4) ? 4 : 1;        // pairs of 8-key n-tiles in this chunk
-        float s[8][4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-          for (int np = 0; np < 4; ++np) {
-            if (np < npairs_n) {
-              const int key = k0 + np * 16 + (lane & 7) + (lane >> 4) * 8;
-              uint32_t bf[4];
-              ldsm_x4(bf, kb + (uint32_t)key * 128u + (uint32_t)(((ks * 2 + ((lane >> 3) & 1)) ^ (key & 7)) * 16));
-              mma16816(s[2 * np], qa[ks], bf[0], bf[1]);
-              mma16816(s[2 * np + 1], qa[ks], bf[2], bf[3]);
-            }
-          }
+        for (int c = 0; c < 8; ++c) {
+          const uint4 u = aptx::ld_shared_u4(kb + (uint32_t)key * 128u + (uint32_t)((c ^ (key & 7)) * 16));
+          const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+          s0 = fmaf(q[c * 8 + 0], f0.x, s0); s1 = fmaf(q[c * 8 + 1], f0.y, s1);
+          s0 = fmaf(q[c * 8 + 2], f1.x, s0); s1 = fmaf(q[c * 8 + 3], f1.y, s1);
+          s0 = fmaf(q[c * 8 + 4], f2.x, s0); s1 = fmaf(q[c * 8 + 5], f2.y, s1);
+          s0 = fmaf(q[c * 8 + 6], f3.x, s0); s1 = fmaf(q[c * 8 + 7], f3.y, s1);
         }
-        float cm = -INFINITY;
+        return s0 + s1;
+      };
+      float t[5];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          if (nt < 2 * npairs_n) {
-            const int key = k0 + nt * 8 + 2 * q4;
-            if (key >= kSeq) s[nt][0] = -INFINITY;
-            if (key + 1 >= kSeq) s[nt][1] = -INFINITY;
-            cm = fmaxf(cm, fmaxf(s[nt][0], s[nt][1]));
-          }
-        }
-        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
-        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
-        const float m_new = fmaxf(m_run, cm);
-        const float corr = aptx::ex2((m_run - m_new) * sc);
-        const float nms = -m_new * sc;
-        float sum = 0.f;
-        uint32_t pa[4][4];
+      for (int i = 0; i < 4; ++i) t[i] = dot_key(tw * 128 + i * 32 + lane);
+      t[4] = -INFINITY;
+      if (tw == 1) {                                  // key 256 (rows 257..271 of the box are not keys of this crop)
+        const float v = dot_key(256 + (lane & 15));
+        if (lane == 0) t[4] = v;
+      }
+      const float m_loc = warp_max(fmaxf(fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3])), t[4]));
+      float l_loc = 0.f;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          if (kk < npairs_n) {
-            const float p00 = aptx::ex2(fmaf(s[2 * kk][0], sc, nms)), p01 = aptx::ex2(fmaf(s[2 * kk][1], sc, nms));
-            const float p10 = aptx::ex2(fmaf(s[2 * kk + 1][0], sc, nms)), p11 = aptx::ex2(fmaf(s[2 * kk + 1][1], sc, nms));
-            sum += (p00 + p01) + (p10 + p11);
-            pa[kk][0] = pack_bf16x2(p00, p01); pa[kk][1] = 0u;       // rows 8..15 of the fragment: zero
-            pa[kk][2] = pack_bf16x2(p10, p11); pa[kk][3] = 0u;
-          }
-        }
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        l_run = l_run * corr + sum;
-        m_run = m_new;
+      for (int i = 0; i < 5; ++i) {
+        const float p = aptx::ex2((t[i] - m_loc) * sc);
+        l_loc += p;
+        if (i < 4) pbuf[i * 32 + lane] = p;
+        else if (lane == 0) pbuf[128] = p;
+      }
+      l_loc = warp_sum(l_loc);
+      __syncwarp();
+      // context: this lane's two feature columns over the warp's keys
+      float acc0 = 0.f, acc1 = 0.f;
+      const uint32_t voff = (uint32_t)((lane & 3) * 4);
+      const int cch = lane >> 2;
+#pragma unroll 4
+      for (int j = 0; j < 128; j += 4) {
+        const float4 pj = *reinterpret_cast<const float4*>(pbuf + j);
+        const float pv[4] = {pj.x, pj.y, pj.z, pj.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { acc[i][0] *= corr; acc[i][1] *= corr; }
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          if (kk < npairs_n) {
-#pragma unroll
-            for (int dp = 0; dp < 4; ++dp) {
-              const int key = k0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-              uint32_t bf[4];
-              ldsm_x4_t(bf, vb + (uint32_t)key * 128u + (uint32_t)(((dp * 2 + (lane >> 4)) ^ (key & 7)) * 16));
-              mma16816(acc[2 * dp], pa[kk], bf[0], bf[1]);
-              mma16816(acc[2 * dp + 1], pa[kk], bf[2], bf[3]);
-            }
-          }
+        for (int u = 0; u < 4; ++u) {
+          const int key = tw * 128 + j + u;
+          uint32_t w;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(vb + (uint32_t)key * 128u + (uint32_t)((cch ^ (key & 7)) * 16) + voff));
+          const float2 f = unpack_bf16x2(w);
+          acc0 = fmaf(pv[u], f.x, acc0);
+          acc1 = fmaf(pv[u], f.y, acc1);
         }
       }
-      __threadfence_block();       // keep the arrive below the last ldmatrix (see cross_absorbed.cu)
+      if (tw == 1) {
+        uint32_t w;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(vb + 256u * 128u + (uint32_t)(cch * 16) + voff));   // key 256: 256 & 7 == 0
+        const float2 f = unpack_bf16x2(w);
+        const float p = pbuf[128];
+        acc0 = fmaf(p, f.x, acc0);
+        acc1 = fmaf(p, f.y, acc1);
+      }
+      __threadfence_block();       // keep the arrive below the last shared-memory read of the staged tiles
       __syncwarp();
       if (lane == 0) aptx::mbar_arrive(KV_EMPTY(buf));
-      if (g == 0) {
-        const float inv = 1.0f / l_run;
-        bf16* orow = a.out + (size_t)b * a.o_bs + (size_t)(kSeq - 1) * a.o_rs + (size_t)h * kAD + 2 * q4;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-          *reinterpret_cast<uint32_t*>(orow + nt * 8) = pack_bf16x2(acc[nt][0] * inv, acc[nt][1] * inv);
+      float* pp = part + (it & 1) * 68;
+      if (tw == 0) {
+        if (lane == 0) { pp[0] = m_loc; pp[1] = l_loc; }
+        pp[2 + 2 * lane] = acc0; pp[3 + 2 * lane] = acc1;
+      }
+      asm volatile("bar.sync 3, 64;" ::: "memory");
+      if (tw == 1) {
+        const float m0 = pp[0], l0 = pp[1];
+        const float m = fmaxf(m0, m_loc);
+        const float a0 = aptx::ex2((m0 - m) * sc), a1 = aptx::ex2((m_loc - m) * sc);
+        const float inv = 1.0f / fmaf(l0, a0, l_loc * a1);
+        const float o0 = fmaf(pp[2 + 2 * lane], a0, acc0 * a1) * inv, o1 = fmaf(pp[3 + 2 * lane], a0, acc1 * a1) * inv;
+        bf16* orow = a.out + (size_t)b * a.o_bs + (size_t)(kSeq - 1) * a.o_rs + (size_t)h * kAD + 2 * lane;
+        *reinterpret_cast<uint32_t*>(orow) = pack_bf16x2(o0, o1);
       }
     }
   } else if (warp >= 4) {
