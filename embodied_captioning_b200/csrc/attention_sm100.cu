@@ -505,38 +505,65 @@ done:
 // needs a 256-column fp32 S buffer, TMEM holds two of them, so each of the two softmax groups runs its tile's chain
 // QK^T -> row max (first read of S) -> exp (second read of S) -> P.V -> O read strictly in series, and the 257th
 // query costs a third, almost empty, tile per (crop, head).  v2 changes the decomposition:
-//   * keys in two blocks of 128 (+ the 257th key as a 16-column MMA), each block's S is read from TMEM ONCE into
-//     registers (128 fp32 per row thread), exponentiated against the block's own row max and written back as P;
-//     the two blocks accumulate into two separate O accumulators that the epilogue combines with the exact
-//     2^(m_b - m) factors -- no rescaling of O in flight, no second pass over S;
-//   * per softmax group TMEM holds S/P (128 columns) + O_a (64) + O_b (64): the S buffer is free as soon as the
-//     block's P.V has been ISSUED (tcgen05.mma executes in issue order), so the next block's / next pair's QK^T is
-//     in flight while the group is still in its epilogue;
+//   * keys in three blocks (96 + 96 + 80 staged rows, the last one masked beyond key 256).  A block's S (96 columns) is
+//     read from TMEM ONCE into registers and the S buffer handed back at once (S_FREE), so the next block's QK^T runs
+//     while this block is exponentiated; P goes to one of two separate 48-column buffers, O is a single 64-column
+//     accumulator (tcgen05.mma accumulates over the blocks);
+//   * online softmax with a LAZY reference: block 0's row max is the reference for the whole row unless a later block
+//     exceeds it by more than 2^8 (then the warp rescales O in TMEM and the running sum: rare, exact either way --
+//     probabilities up to 256 are harmless in bf16 / fp32 and the final 1 / l uses the same reference);
 //   * group g always owns query tile g of the pair (queries 128 g .. 128 g + 127): no third tile.  The 257th query is
-//     one row: two spare warps run it on the fp32 pipe straight from the staged K / V;
-//   * one warp issues every tcgen05.mma (in-order hazards on the aliased TMEM columns need a single issuer).
-// TMEM columns of group g (base 256 g): [0,128) S block / P (bf16, 64 columns; + 8 columns for the 257th key),
-// [128,192) O_a, [192,256) O_b; the 257th key's score column lands in O_b's first 16 columns before O_b is written.
+//     one row: a spare warp runs it on the fp32 pipe straight from the staged K / V;
+//   * one MMA-issuing warp PER GROUP (the in-order hazards on a group's TMEM columns need one issuer per group; each
+//     warp blocks on its own group's barriers in their fixed order.  Measured alternatives: one warp polling both
+//     groups answered every event ~1 k cycles late (0.77 ms per layer); the group's first softmax warp issuing the
+//     MMAs itself put its own softmax work on everybody's critical path (1.04 ms)).
+// TMEM columns of group g (base 256 g): [0,96) S block, [96,144) P (even blocks), [144,192) P (odd blocks), [192,256) O.
 //
-//   warp 0: TMA producer | warp 1: MMA issuer | warps 2-3: 257th query (warp 2 also owns the TMEM allocation)
-//   | warps 4-7: softmax group 0 | warps 8-11: softmax group 1
+//   warp 0: TMA producer | warps 1-2: MMA issuers of group 0 / 1 (warp 2 also owns the TMEM allocation)
+//   | warp 3: 257th query | warps 4-7: softmax group 0 | warps 8-11: softmax group 1
 namespace av2 {
 
 constexpr int kSeq = 257;
 constexpr int kThreads = 12 * 32;
+constexpr int kBlk = 96;                                 // keys of blocks 0 and 1
+constexpr int kBlkLast = 80;                             // staged rows 192..271 (keys 192..256 + 15 rows of padding)
 constexpr int kKvBytes = 2 * kAKBytes + 2048;            // K (272 rows) | V (272 rows) | 16-row box holding query 256
-constexpr int kSmemBytes = 2 * kKvBytes + 4 * kAQBytes + 3072 + 1024;   // + barriers, 257th-query scratch, alignment
-static_assert(kKvBytes % 1024 == 0 && kAKBytes % 1024 == 0, "SW128 operands need 1024-byte aligned bases");
+constexpr int kTailPartFloats = 100;                      // a warp's partial of the 257th query: m, l, (pad), acc[64]; + its 32 probabilities
+constexpr int kSmemBytes = 2 * kKvBytes + 4 * kAQBytes + 8192 + 1024;   // + barriers, 257th-query partials, alignment
+constexpr float kRescaleGap = 8.0f;                      // log2 units a later block's max may exceed the reference by
+static_assert(kKvBytes % 1024 == 0 && kAKBytes % 1024 == 0 && (kBlk * 128) % 1024 == 0, "SW128 operands need 1024-byte aligned bases");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
+static_assert(2 * kBlk + kBlkLast == kAKeysMma + kAKeysTail, "the three key blocks cover the staged rows exactly");
 
-__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-}
+#ifdef EC_ATTN_TIMING
+#define EC_TICK(var) const long long var = clock64()
+#else
+#define EC_TICK(var)
+#endif
+
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
-// exp of 32 score columns against the block's row max: P (bf16) -> 16 TMEM columns, running sum in `sum2`
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+// exp of 32 score columns against the row's reference: P (bf16) -> 16 TMEM columns, running sum in `sum2`
 __device__ __forceinline__ void exp_chunk(const uint32_t (&v)[32], uint64_t sc2, uint64_t nms2, uint64_t& sum2, uint32_t taddr) {
   uint32_t pk[16];
 #pragma unroll
@@ -549,8 +576,8 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&v)[32], uint64_t sc2,
   }
   aptx::tmem_st16(taddr, pk);
 }
-__device__ __forceinline__ float max_chunk(const uint32_t (&v)[32], float mx) {
-  float m0 = mx, m1 = -INFINITY;
+__device__ __forceinline__ float max_chunk(const uint32_t (&v)[32]) {
+  float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     m0 = aptx::max3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
@@ -560,7 +587,8 @@ __device__ __forceinline__ float max_chunk(const uint32_t (&v)[32], float mx) {
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-attention257_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16, AttnSm100Args a) {
+attention257_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16,
+                    const __grid_constant__ CUtensorMap tm_out, AttnSm100Args a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   auto k_smem = [&](int buf) { return base + (uint32_t)buf * kKvBytes; };
@@ -574,28 +602,41 @@ attention257_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_cons
   auto Q_FULL = [&](int g, int b) { return bar0 + 8u * (uint32_t)(4 + g * 2 + b); };
   auto Q_EMPTY = [&](int g, int b) { return bar0 + 8u * (uint32_t)(8 + g * 2 + b); };
   auto S_FULL = [&](int g) { return bar0 + 8u * (uint32_t)(12 + g); };
-  auto P_READY = [&](int g) { return bar0 + 8u * (uint32_t)(14 + g); };
-  auto O_FULL = [&](int g) { return bar0 + 8u * (uint32_t)(16 + g); };
+  auto S_FREE = [&](int g) { return bar0 + 8u * (uint32_t)(14 + g); };
+  auto P_READY = [&](int g) { return bar0 + 8u * (uint32_t)(16 + g); };
   auto O_FREE = [&](int g) { return bar0 + 8u * (uint32_t)(18 + g); };
-  const uint32_t tmem_slot = bar0 + 8u * 24u;
+  auto PV_DONE = [&](int g, int b) { return bar0 + 8u * (uint32_t)(20 + g * 2 + b); };     // P.V of an even / odd block completed
+  auto TAIL_FULL = [&](int b) { return bar0 + 8u * (uint32_t)(24 + b); };    // the 8 partials of the 257th query are written
+  auto TAIL_EMPTY = [&](int b) { return bar0 + 8u * (uint32_t)(26 + b); };   // ... and merged
+  auto OUT_READY = [&](int g) { return bar0 + 8u * (uint32_t)(28 + g); };    // the tile's output rows are staged in shared memory
+  auto P_TAKEN = [&](int g) { return bar0 + 8u * (uint32_t)(30 + g); };      // the issuer has consumed a P_READY phase
+  const uint32_t tmem_slot = bar0 + 8u * 32u;
+  float* tail_part = reinterpret_cast<float*>(smem_raw + (bar0 + 512u - smem_u32(smem_raw)));   // [2][8][kTailPartFloats]
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_pairs = a.batch * a.heads;
+  const int heads = a.heads;
+  const int n_pairs = a.batch * heads;
+  const int grid = (int)gridDim.x;
 
-  if (warp == 0 && lane == 0) { aptx::prefetch_tmap(&tm128); aptx::prefetch_tmap(&tm16); }
+  if (warp == 0 && lane == 0) { aptx::prefetch_tmap(&tm128); aptx::prefetch_tmap(&tm16); aptx::prefetch_tmap(&tm_out); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       aptx::mbar_init(KV_FULL(i), 1);
-      aptx::mbar_init(KV_EMPTY(i), 4);         // last P.V commit of either group + the two 257th-query warps
+      aptx::mbar_init(KV_EMPTY(i), 11);        // last P.V commit of either group + 8 softmax warps + the merging warp (257th query)
+      aptx::mbar_init(TAIL_FULL(i), 8);
+      aptx::mbar_init(TAIL_EMPTY(i), 1);
       for (int g = 0; g < 2; ++g) {
         aptx::mbar_init(Q_FULL(g, i), 1);
-        aptx::mbar_init(Q_EMPTY(g, i), 1);     // commit after the tile's last QK^T
+        aptx::mbar_init(Q_EMPTY(g, i), 1);     // the tile's output has left the buffer (it doubles as the store staging)
+        aptx::mbar_init(PV_DONE(g, i), 1);
       }
       aptx::mbar_init(S_FULL(i), 1);
+      aptx::mbar_init(S_FREE(i), 128);
       aptx::mbar_init(P_READY(i), 128);
-      aptx::mbar_init(O_FULL(i), 1);
       aptx::mbar_init(O_FREE(i), 128);
+      aptx::mbar_init(OUT_READY(i), 128);
+      aptx::mbar_init(P_TAKEN(i), 1);
     }
     aptx::fence_barrier_init();
   }
@@ -608,8 +649,8 @@ attention257_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_cons
   if (warp == 0) {
     // ============================================================ TMA producer
     uint32_t it = 0;
-    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
-      const int b = pair / a.heads, h = pair % a.heads;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += grid, ++it) {
+      const int b = pair / heads, h = pair % heads;
       const int row0 = b * kSeq;
       const int buf = it & 1;
       const uint32_t par_empty = ((it >> 1) & 1) ^ 1u;
@@ -636,181 +677,146 @@ attention257_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_cons
         __syncwarp();
       }
     }
-  } else if (warp == 1) {
-    // ============================================================ MMA issuer (every tcgen05.mma of the CTA, in order)
-    const uint32_t id_qk = idesc_qk(128), id_qt = idesc_qk(16), id_pv = idesc_pv();
-    auto issue_qk = [&](uint32_t t_d, uint32_t q_addr, uint32_t k_addr, uint32_t idesc) {
+  } else if (warp == 1 || warp == 2) {
+    // ============================================================ MMA issuer of group g: its group's events come in a
+    // fixed order -- S_FREE(0) P_READY(0) S_FREE(1) P_READY(1) S_FREE(2) P_READY(2) per tile -- so plain blocking waits do
+    const int g = warp - 1;
+    const uint32_t tg = tmem_base + (uint32_t)(g * 256);
+    const uint32_t id_qk = idesc_qk(kBlk), id_qk_last = idesc_qk(kBlkLast), id_pv = idesc_pv();
+    auto issue_qk = [&](uint32_t q_addr, uint32_t k_addr, uint32_t idesc) {
       const uint64_t qdesc = desc_kmajor(q_addr), kdesc = desc_kmajor(k_addr);
 #pragma unroll
       for (int k = 0; k < kAD / 16; ++k)
-        aptx::umma_ss(t_d, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc, k > 0 ? 1u : 0u);
+        aptx::umma_ss(tg, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc, k > 0 ? 1u : 0u);
     };
-    auto issue_pv = [&](uint32_t t_d, uint32_t t_p, uint32_t v_addr, int ksteps) {
-      const uint64_t vdesc0 = desc_mnmajor(v_addr);
-      for (int k = 0; k < ksteps; ++k)
-        aptx::umma_ts(t_d, t_p + (uint32_t)(k * 8), vdesc0 + (uint64_t)(k * (2048 >> 4)), id_pv, k > 0 ? 1u : 0u);
-    };
-    uint32_t it = 0, p_cnt[2] = {0u, 0u};
-    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t par = (it >> 1) & 1;
-      if (it == 0) {
-        if (!await(KV_FULL(0), 0, 3)) goto done;
-        for (int g = 0; g < 2; ++g) {
-          if (!await(Q_FULL(g, 0), 0, 4)) goto done;
-          aptx::tc_fence_after();
-          if (aptx::elect_one()) {
-            issue_qk(tmem_base + (uint32_t)(g * 256), q_smem(g, 0), k_smem(0), id_qk);
-            aptx::umma_commit(S_FULL(g));
-          }
-          __syncwarp();
-        }
+    uint32_t it = 0;
+    if ((int)blockIdx.x < n_pairs) {
+      if (!await(KV_FULL(0), 0, 3)) goto done;
+      if (!await(Q_FULL(g, 0), 0, 4)) goto done;
+      aptx::tc_fence_after();
+      if (aptx::elect_one()) {
+        issue_qk(q_smem(g, 0), k_smem(0), id_qk);
+        aptx::umma_commit(S_FULL(g));
       }
-      // key block 0 consumed -> O_a = P_0 V_0, the 257th key's scores, S_1 = Q K_1^T
-      for (int g = 0; g < 2; ++g) {
-        if (!await(P_READY(g), p_cnt[g] & 1, 5)) goto done;
-        ++p_cnt[g];
-        if (!await(O_FREE(g), (it & 1) ^ 1u, 6)) goto done;      // the previous tile's epilogue has read O_a / O_b
-        aptx::tc_fence_after();
-        const uint32_t tg = tmem_base + (uint32_t)(g * 256);
-        if (aptx::elect_one()) {
-          issue_pv(tg + 128u, tg, v_smem(buf), 8);
-          issue_qk(tg + 192u, q_smem(g, buf), k_smem(buf) + 2 * kAQBytes, id_qt);
-          issue_qk(tg, q_smem(g, buf), k_smem(buf) + kAQBytes, id_qk);
-          aptx::umma_commit(S_FULL(g));
-          aptx::umma_commit(Q_EMPTY(g, buf));
-        }
-        __syncwarp();
-      }
-      // key block 1 (+ the 257th key) consumed -> O_b = P_1 V_1; then the next pair's first QK^T into the freed S buffer
-      const bool has_next = pair + (int)gridDim.x < n_pairs;
-      const int nbuf = buf ^ 1;
-      const uint32_t npar = ((it + 1) >> 1) & 1;
-      for (int g = 0; g < 2; ++g) {
-        if (!await(P_READY(g), p_cnt[g] & 1, 7)) goto done;
-        ++p_cnt[g];
-        aptx::tc_fence_after();
-        const uint32_t tg = tmem_base + (uint32_t)(g * 256);
-        if (aptx::elect_one()) {
-          issue_pv(tg + 192u, tg, v_smem(buf) + kAQBytes, 9);
-          aptx::umma_commit(O_FULL(g));
-          aptx::umma_commit(KV_EMPTY(buf));
-        }
-        __syncwarp();
-        if (has_next) {
-          if (g == 0 && !await(KV_FULL(nbuf), npar, 8)) goto done;
-          if (!await(Q_FULL(g, nbuf), npar, 9)) goto done;
-          aptx::tc_fence_after();
-          if (aptx::elect_one()) {
-            issue_qk(tg, q_smem(g, nbuf), k_smem(nbuf), id_qk);
-            aptx::umma_commit(S_FULL(g));
-          }
-          __syncwarp();
-        }
-      }
-      (void)par;
+      __syncwarp();
     }
-  } else if (warp == 2 || warp == 3) {
-    // ============================================================ the 257th query: one row, on the fp32 pipe of two
-    // spare warps (warp 2: keys 0..127, warp 3: keys 128..256).  Scores: a lane per key (K rows straight from the staged
-    // tile); context: a lane per pair of feature columns, the warp's probabilities broadcast from shared memory; warp 3
-    // merges the two partial softmaxes.  (Measured: the same row as a 16 x 272 x 64 mma.sync flash attention on ONE warp
-    // took 13 k cycles per (crop, head) -- legacy HMMA at ~48 cycles each -- and was the critical path of the CTA.)
-    const int tw = warp - 2;
-    float* tail_f = reinterpret_cast<float*>(smem_raw + (bar0 + 256u - smem_u32(smem_raw)));
-    float* pbuf = tail_f + tw * 132;                 // this warp's probabilities [129]
-    float* part = tail_f + 2 * 132;                  // warp 2's partial (m, l, acc[64]), double-buffered by pair parity
+    for (int pair = blockIdx.x; pair < n_pairs; pair += grid, ++it) {
+      const int buf = it & 1, nbuf = buf ^ 1;
+      const bool has_next = pair + grid < n_pairs;
+      const uint32_t npar = ((it + 1) >> 1) & 1;
+      bool next_issued = false;
+#pragma unroll
+      for (int blk = 0; blk < 3; ++blk) {
+        const uint32_t n = 3u * it + (uint32_t)blk;
+        // ---- S of block `blk` is in registers -> QK^T of the next block (or of the next pair's first one)
+        if (!await(S_FREE(g), n & 1u, 5)) goto done;
+        aptx::tc_fence_after();
+        if (blk < 2) {
+          if (aptx::elect_one()) {
+            issue_qk(q_smem(g, buf), k_smem(buf) + (uint32_t)((blk + 1) * kBlk * 128), blk == 1 ? id_qk_last : id_qk);
+            aptx::umma_commit(S_FULL(g));
+          }
+          __syncwarp();
+        } else if (has_next && aptx::mbar_try_wait(KV_FULL(nbuf), npar) && aptx::mbar_try_wait(Q_FULL(g, nbuf), npar)) {
+          // (not staged yet: issued after this tile's last P.V instead, so that P.V is never held up)
+          if (aptx::elect_one()) {
+            issue_qk(q_smem(g, nbuf), k_smem(nbuf), id_qk);
+            aptx::umma_commit(S_FULL(g));
+          }
+          __syncwarp();
+          next_issued = true;
+        }
+        // ---- P of block `blk` is in TMEM -> O (+)= P V
+        if (!await(P_READY(g), n & 1u, 7)) goto done;
+        if (lane == 0) aptx::mbar_arrive(P_TAKEN(g));              // the group may publish the next block's P
+#ifdef EC_ATTN_TIMING
+        const long long t_obs = clock64();
+#endif
+        if (blk == 0 && !await(O_FREE(g), (it & 1) ^ 1u, 6)) goto done;    // the previous tile's epilogue has read O
+        aptx::tc_fence_after();
+        if (aptx::elect_one()) {
+          const uint64_t vdesc0 = desc_mnmajor(v_smem(buf) + (uint32_t)(blk * kBlk * 128));
+          const uint32_t t_p = tg + 96u + (n & 1u) * 48u;
+          const int ksteps = (blk == 2) ? kBlkLast / 16 : kBlk / 16;
+          for (int k = 0; k < ksteps; ++k)
+            aptx::umma_ts(tg + 192u, t_p + (uint32_t)(k * 8), vdesc0 + (uint64_t)(k * (2048 >> 4)), id_pv, (k > 0 || blk > 0) ? 1u : 0u);
+          aptx::umma_commit(PV_DONE(g, (int)(n & 1u)));
+          if (blk == 2) aptx::umma_commit(KV_EMPTY(buf));
+#ifdef EC_ATTN_TIMING
+          long long* ts = reinterpret_cast<long long*>(smem_raw + (bar0 + 7168u - smem_u32(smem_raw))) + (g * 2 + (int)(n & 1u)) * 2;
+          ts[0] = t_obs; ts[1] = clock64();
+#endif
+        }
+        __syncwarp();
+      }
+      // ---- the tile's output rows are staged in its Q buffer -> one bulk tensor store; the buffer goes back to the
+      // producer (for pair it + 2) once the store has read it
+      if (!await(OUT_READY(g), it & 1u, 17)) goto done;
+      if (aptx::elect_one()) {
+        const int b = pair / heads, h = pair % heads;
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                     ::"l"(&tm_out), "r"(h * kAD), "r"(b * kSeq + g * kATile), "r"(q_smem(g, buf)) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        aptx::mbar_arrive(Q_EMPTY(g, buf));
+      }
+      __syncwarp();
+      if (has_next && !next_issued) {
+        if (!await(KV_FULL(nbuf), npar, 8)) goto done;
+        if (!await(Q_FULL(g, nbuf), npar, 9)) goto done;
+        aptx::tc_fence_after();
+        if (aptx::elect_one()) {
+          issue_qk(q_smem(g, nbuf), k_smem(nbuf), id_qk);
+          aptx::umma_commit(S_FULL(g));
+        }
+        __syncwarp();
+      }
+    }
+    if (aptx::elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // this lane's bulk stores have landed
+    __syncwarp();
+  } else if (warp == 3) {
+    // ============================================================ the 257th query, merging warp.  The row's attention
+    // is computed on the fp32 pipe straight from the staged K / V: every softmax warp takes 32 keys in the slot where it
+    // would otherwise wait for its tile's last P.V (scores: a lane per key; context: a lane per pair of feature columns)
+    // and leaves a partial (m, l, acc[64]); this warp adds key 256 and merges.  (Measured: the whole row on this one
+    // warp made its scheduler's two softmax warps ~1.2 k cycles per (crop, head) slower than the other six, and both
+    // groups wait for their slowest warp three times per tile; as a 16 x 272 x 64 mma.sync flash attention it took
+    // 13 k cycles -- legacy HMMA at ~48 cycles each.)
     const float sc = a.scale_log2;
     uint32_t it = 0;
-    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
-      const int b = pair / a.heads, h = pair % a.heads;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += grid, ++it) {
+      const int b = pair / heads, h = pair % heads;
       const int buf = it & 1;
       if (!await(KV_FULL(buf), (it >> 1) & 1, 10)) goto done;
-      const uint32_t kb = k_smem(buf), vb = v_smem(buf), qb = qt_smem(buf);
-      float q[kAD];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint4 u = aptx::ld_shared_u4(qb + (uint32_t)(c * 16));          // row 0 of the box: swizzle term is 0
-        const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-        q[c * 8 + 0] = f0.x; q[c * 8 + 1] = f0.y; q[c * 8 + 2] = f1.x; q[c * 8 + 3] = f1.y;
-        q[c * 8 + 4] = f2.x; q[c * 8 + 5] = f2.y; q[c * 8 + 6] = f3.x; q[c * 8 + 7] = f3.y;
-      }
-      auto dot_key = [&](int key) {
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 u = aptx::ld_shared_u4(kb + (uint32_t)key * 128u + (uint32_t)((c ^ (key & 7)) * 16));
-          const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-          s0 = fmaf(q[c * 8 + 0], f0.x, s0); s1 = fmaf(q[c * 8 + 1], f0.y, s1);
-          s0 = fmaf(q[c * 8 + 2], f1.x, s0); s1 = fmaf(q[c * 8 + 3], f1.y, s1);
-          s0 = fmaf(q[c * 8 + 4], f2.x, s0); s1 = fmaf(q[c * 8 + 5], f2.y, s1);
-          s0 = fmaf(q[c * 8 + 6], f3.x, s0); s1 = fmaf(q[c * 8 + 7], f3.y, s1);
-        }
-        return s0 + s1;
-      };
-      float t[5];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) t[i] = dot_key(tw * 128 + i * 32 + lane);
-      t[4] = -INFINITY;
-      if (tw == 1) {                                  // key 256 (rows 257..271 of the box are not keys of this crop)
-        const float v = dot_key(256 + (lane & 15));
-        if (lane == 0) t[4] = v;
-      }
-      const float m_loc = warp_max(fmaxf(fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3])), t[4]));
-      float l_loc = 0.f;
-#pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const float p = aptx::ex2((t[i] - m_loc) * sc);
-        l_loc += p;
-        if (i < 4) pbuf[i * 32 + lane] = p;
-        else if (lane == 0) pbuf[128] = p;
-      }
-      l_loc = warp_sum(l_loc);
-      __syncwarp();
-      // context: this lane's two feature columns over the warp's keys
-      float acc0 = 0.f, acc1 = 0.f;
-      const uint32_t voff = (uint32_t)((lane & 3) * 4);
-      const int cch = lane >> 2;
-#pragma unroll 4
-      for (int j = 0; j < 128; j += 4) {
-        const float4 pj = *reinterpret_cast<const float4*>(pbuf + j);
-        const float pv[4] = {pj.x, pj.y, pj.z, pj.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int key = tw * 128 + j + u;
-          uint32_t w;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(vb + (uint32_t)key * 128u + (uint32_t)((cch ^ (key & 7)) * 16) + voff));
-          const float2 f = unpack_bf16x2(w);
-          acc0 = fmaf(pv[u], f.x, acc0);
-          acc1 = fmaf(pv[u], f.y, acc1);
-        }
-      }
-      if (tw == 1) {
-        uint32_t w;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(vb + 256u * 128u + (uint32_t)(cch * 16) + voff));   // key 256: 256 & 7 == 0
-        const float2 f = unpack_bf16x2(w);
-        const float p = pbuf[128];
-        acc0 = fmaf(p, f.x, acc0);
-        acc1 = fmaf(p, f.y, acc1);
-      }
-      __threadfence_block();       // keep the arrive below the last shared-memory read of the staged tiles
+      // key 256: this lane's two feature columns of q, k and v (row 0 of each 16-row box: the swizzle term is 0)
+      uint32_t wq, wk, wv;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wq) : "r"(qt_smem(buf) + (uint32_t)(lane * 4)));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wk) : "r"(k_smem(buf) + 256u * 128u + (uint32_t)(lane * 4)));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv) : "r"(v_smem(buf) + 256u * 128u + (uint32_t)(lane * 4)));
+      __threadfence_block();
       __syncwarp();
       if (lane == 0) aptx::mbar_arrive(KV_EMPTY(buf));
-      float* pp = part + (it & 1) * 68;
-      if (tw == 0) {
-        if (lane == 0) { pp[0] = m_loc; pp[1] = l_loc; }
-        pp[2 + 2 * lane] = acc0; pp[3 + 2 * lane] = acc1;
+      const float2 fq = unpack_bf16x2(wq), fk = unpack_bf16x2(wk), fv = unpack_bf16x2(wv);
+      const float t256 = warp_sum(fmaf(fq.x, fk.x, fq.y * fk.y));
+      if (!await(TAIL_FULL(buf), (it >> 1) & 1, 14)) goto done;
+      const float* pp = tail_part + buf * 8 * kTailPartFloats;
+      float m = t256;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) m = fmaxf(m, pp[w * kTailPartFloats]);
+      const float p256 = aptx::ex2((t256 - m) * sc);
+      float l = p256, o0 = p256 * fv.x, o1 = p256 * fv.y;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const float aw = aptx::ex2((pp[w * kTailPartFloats] - m) * sc);
+        l = fmaf(pp[w * kTailPartFloats + 1], aw, l);
+        o0 = fmaf(pp[w * kTailPartFloats + 4 + 2 * lane], aw, o0);
+        o1 = fmaf(pp[w * kTailPartFloats + 5 + 2 * lane], aw, o1);
       }
-      asm volatile("bar.sync 3, 64;" ::: "memory");
-      if (tw == 1) {
-        const float m0 = pp[0], l0 = pp[1];
-        const float m = fmaxf(m0, m_loc);
-        const float a0 = aptx::ex2((m0 - m) * sc), a1 = aptx::ex2((m_loc - m) * sc);
-        const float inv = 1.0f / fmaf(l0, a0, l_loc * a1);
-        const float o0 = fmaf(pp[2 + 2 * lane], a0, acc0 * a1) * inv, o1 = fmaf(pp[3 + 2 * lane], a0, acc1 * a1) * inv;
-        bf16* orow = a.out + (size_t)b * a.o_bs + (size_t)(kSeq - 1) * a.o_rs + (size_t)h * kAD + 2 * lane;
-        *reinterpret_cast<uint32_t*>(orow) = pack_bf16x2(o0, o1);
-      }
+      __syncwarp();
+      if (lane == 0) aptx::mbar_arrive(TAIL_EMPTY(buf));
+      const float inv = 1.0f / l;
+      bf16* orow = a.out + (size_t)b * a.o_bs + (size_t)(kSeq - 1) * a.o_rs + (size_t)h * kAD + 2 * lane;
+      *reinterpret_cast<uint32_t*>(orow) = pack_bf16x2(o0 * inv, o1 * inv);
     }
   } else if (warp >= 4) {
     // ============================================================ softmax + epilogue: one thread per query row
@@ -820,79 +826,189 @@ attention257_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_cons
     const uint32_t tg = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * 256);
     const float sc = a.scale_log2;
     const uint64_t sc2 = aptx::pack_f32x2(sc, sc);
-    uint32_t it = 0, s_cnt = 0;
-    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
-      const int b = pair / a.heads, h = pair % a.heads;
-      float ms[2], l[2];
+    auto wait_pv = [&](uint32_t n) { return await(PV_DONE(grp, (int)(n & 1u)), (n >> 1) & 1u, 13); };   // P.V of block n complete
+#ifdef EC_ATTN_TIMING
+    long long tm_s = 0, tm_ld = 0, tm_exp = 0, tm_bp = 0, tm_epi_wait = 0, tm_epi = 0, tm_total = clock64(), t_arr = 0, tm_h1 = 0, tm_h2 = 0, tm_h3 = 0;
+#endif
+    uint32_t it = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += grid, ++it) {
+      const int b = pair / heads, h = pair % heads;
+      const int buf = it & 1;
+      float m_ref = 0.f, l = 0.f;
 #pragma unroll
-      for (int blk = 0; blk < 2; ++blk) {
-        if (!await(S_FULL(grp), s_cnt & 1, 11)) goto done;
-        ++s_cnt;
+      for (int blk = 0; blk < 3; ++blk) {
+        const uint32_t n = 3u * it + (uint32_t)blk;           // running block number: S_FULL phase, P buffer parity
+        EC_TICK(c0);
+        if (!await(S_FULL(grp), n & 1u, 11)) goto done;
+        EC_TICK(c1);
         aptx::tc_fence_after();
-        uint32_t v0[32], v1[32], v2[32], v3[32], vt = 0u;
+        uint32_t v0[32], v1[32], v2[32];
         aptx::tmem_ld32(tg, v0);
         aptx::tmem_ld32(tg + 32u, v1);
-        aptx::tmem_ld32(tg + 64u, v2);
-        aptx::tmem_ld32(tg + 96u, v3);
-        if (blk == 1) tmem_ld1(tg + 192u, vt);
-        aptx::tmem_ld_wait();
-        float mx = (blk == 1) ? __uint_as_float(vt) : -INFINITY;
-        mx = max_chunk(v0, mx);
-        mx = fmaxf(mx, max_chunk(v1, -INFINITY));
-        mx = fmaxf(mx, max_chunk(v2, -INFINITY));
-        mx = fmaxf(mx, max_chunk(v3, -INFINITY));
-        const float m_s = mx * sc;
-        const uint64_t nms2 = aptx::pack_f32x2(-m_s, -m_s);
-        uint64_t sum2 = aptx::pack_f32x2(0.f, 0.f);
-        exp_chunk(v0, sc2, nms2, sum2, tg);
-        exp_chunk(v1, sc2, nms2, sum2, tg + 16u);
-        exp_chunk(v2, sc2, nms2, sum2, tg + 32u);
-        exp_chunk(v3, sc2, nms2, sum2, tg + 48u);
-        float s_lo, s_hi;
-        aptx::unpack_f32x2(sum2, s_lo, s_hi);
-        float sum = s_lo + s_hi;
-        if (blk == 1) {
-          const float pt = aptx::ex2(fmaf(__uint_as_float(vt), sc, -m_s));
-          sum += pt;
-          const uint32_t pk[8] = {pack_bf16x2(pt, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};     // keys 256 | 257..271 (padding)
-          tmem_st8(tg + 64u, pk);
+        if (blk < 2) {
+          aptx::tmem_ld32(tg + 64u, v2);
+        } else {
+          uint32_t vt[16];
+          tmem_ld16(tg + 64u, vt);
+          aptx::tmem_ld_wait();
+          v2[0] = vt[0];                                        // column 64 of the last block = key 256; 65..79 are padding rows
         }
-        ms[blk] = m_s;
-        l[blk] = sum;
+        aptx::tmem_ld_wait();
+        aptx::tc_fence_before();
+        aptx::mbar_arrive(S_FREE(grp));                         // S is in registers: the next QK^T may overwrite the buffer
+        EC_TICK(c2);
+        float mx = fmaxf(max_chunk(v0), max_chunk(v1));
+        mx = (blk < 2) ? fmaxf(mx, max_chunk(v2)) : fmaxf(mx, __uint_as_float(v2[0]));
+        const float x_max = mx * sc;
+        if (blk == 0) {
+          m_ref = x_max;
+        } else {
+          const bool grow = x_max > m_ref + kRescaleGap;
+          if (__any_sync(0xffffffffu, grow)) {
+            // rare: rescale this warp's rows of O and the running sums to the new reference (factor 1 for the other rows)
+            if (!wait_pv(n - 1u)) goto done;
+            aptx::tc_fence_after();
+            const float f = grow ? aptx::ex2(m_ref - x_max) : 1.0f;
+            uint32_t o[32];
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              aptx::tmem_ld32(tg + 192u + (uint32_t)(hlf * 32), o);
+              aptx::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
+              tmem_st32(tg + 192u + (uint32_t)(hlf * 32), o);
+            }
+            l *= f;
+            if (grow) m_ref = x_max;
+          }
+        }
+        if (n > 1u && !wait_pv(n - 2u)) goto done;             // this P buffer was last read by the P.V of block n - 2
+        const uint64_t nms2 = aptx::pack_f32x2(-m_ref, -m_ref);
+        uint64_t sum2 = aptx::pack_f32x2(0.f, 0.f);
+        const uint32_t tp = tg + 96u + (n & 1u) * 48u;
+        exp_chunk(v0, sc2, nms2, sum2, tp);
+        exp_chunk(v1, sc2, nms2, sum2, tp + 16u);
+        float s_lo, s_hi;
+        if (blk < 2) {
+          exp_chunk(v2, sc2, nms2, sum2, tp + 32u);
+          aptx::unpack_f32x2(sum2, s_lo, s_hi);
+        } else {
+          const float pt = aptx::ex2(fmaf(__uint_as_float(v2[0]), sc, -m_ref));
+          const uint32_t pk[8] = {pack_bf16x2(pt, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};     // key 256 | rows 257..271 (padding)
+          tmem_st8(tp + 32u, pk);
+          aptx::unpack_f32x2(sum2, s_lo, s_hi);
+          s_lo += pt;
+        }
+        l += s_lo + s_hi;
         aptx::tmem_st_wait();
+        EC_TICK(c3);
+        // Back-pressure: block n's P is only published once the issuer has consumed the P_READY phase of block n - 1 --
+        // it waits by parity (two unseen completions would look like none) and a fast warp must not arrive twice on one
+        // phase.  In steady state that happened a whole block ago.
+        if (n > 0u && !await(P_TAKEN(grp), (n - 1u) & 1u, 18)) goto done;
         aptx::tc_fence_before();
         aptx::mbar_arrive(P_READY(grp));
+        EC_TICK(c4);
+#ifdef EC_ATTN_TIMING
+        t_arr = c4;
+#endif
+#ifdef EC_ATTN_TIMING
+        tm_s += c1 - c0; tm_ld += c2 - c1; tm_exp += c3 - c2; tm_bp += c4 - c3;
+#endif
       }
-      // ---- epilogue: o = (O_a 2^(m_a - m) + O_b 2^(m_b - m)) / (l_a 2^(m_a - m) + l_b 2^(m_b - m))
-      const float m = fmaxf(ms[0], ms[1]);
-      const float a0 = aptx::ex2(ms[0] - m), a1 = aptx::ex2(ms[1] - m);
-      const float inv = 1.0f / fmaf(l[0], a0, l[1] * a1);
-      const float c0 = a0 * inv, c1 = a1 * inv;
-      if (!await(O_FULL(grp), it & 1, 12)) goto done;
+      // ---- this warp's 32 keys of the 257th query (the tile's last P.V is in flight meanwhile)
+      {
+        const int sw = warp - 4;
+        const uint32_t kvpar = (it >> 1) & 1u;
+        if (!await(KV_FULL(buf), kvpar, 15)) goto done;            // long complete: acquires the staged tiles for generic loads
+        const uint32_t kb = k_smem(buf), vb = v_smem(buf), qb = qt_smem(buf);
+        const int key = sw * 32 + lane;
+        // scores: a lane per key; all sixteen 16-byte loads are issued before the first multiply
+        uint4 uq[8], uk[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) uq[c] = aptx::ld_shared_u4(qb + (uint32_t)(c * 16));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) uk[c] = aptx::ld_shared_u4(kb + (uint32_t)key * 128u + (uint32_t)((c ^ (key & 7)) * 16));
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float2 q0 = unpack_bf16x2(uq[c].x), q1 = unpack_bf16x2(uq[c].y), q2 = unpack_bf16x2(uq[c].z), q3 = unpack_bf16x2(uq[c].w);
+          const float2 k0 = unpack_bf16x2(uk[c].x), k1 = unpack_bf16x2(uk[c].y), k2 = unpack_bf16x2(uk[c].z), k3 = unpack_bf16x2(uk[c].w);
+          s0 = fmaf(q0.x, k0.x, s0); s1 = fmaf(q0.y, k0.y, s1); s2 = fmaf(q1.x, k1.x, s2); s3 = fmaf(q1.y, k1.y, s3);
+          s0 = fmaf(q2.x, k2.x, s0); s1 = fmaf(q2.y, k2.y, s1); s2 = fmaf(q3.x, k3.x, s2); s3 = fmaf(q3.y, k3.y, s3);
+        }
+        const float t = (s0 + s1) + (s2 + s3);
+        const float m_w = warp_max(t);
+        const float p = aptx::ex2((t - m_w) * sc);
+        const float l_w = warp_sum(p);
+        // context: half-warp hf takes the keys of parity hf, lane (hf, d4) the four feature columns 4 d4 .. 4 d4 + 3
+        if (!await(TAIL_EMPTY(buf), kvpar ^ 1u, 16)) goto done;    // the merge of pair it - 2 has read this slot
+        float* pp = tail_part + (buf * 8 + sw) * kTailPartFloats;
+        pp[68 + lane] = p;                                          // probabilities [32] behind the 68-float partial
+        __syncwarp();
+        const int hf = lane >> 4, d4 = lane & 15;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const uint32_t vrow = vb + (uint32_t)(sw * 32 + hf) * 128u + (uint32_t)((d4 & 1) * 8);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int kk = 2 * j + hf;                               // key inside the warp's 32 (sw * 32 is a multiple of 8)
+          uint32_t w0, w1;
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1)
+                       : "r"(vrow + (uint32_t)(2 * j) * 128u + (uint32_t)(((d4 >> 1) ^ (kk & 7)) * 16)));
+          const float pj = pp[68 + kk];
+          const float2 f0 = unpack_bf16x2(w0), f1 = unpack_bf16x2(w1);
+          a0 = fmaf(pj, f0.x, a0); a1 = fmaf(pj, f0.y, a1); a2 = fmaf(pj, f1.x, a2); a3 = fmaf(pj, f1.y, a3);
+        }
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 16); a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, 16); a3 += __shfl_xor_sync(0xffffffffu, a3, 16);
+        __threadfence_block();       // keep the arrives below the last shared-memory read of the staged tiles
+        if (lane == 0) { pp[0] = m_w; pp[1] = l_w; }
+        if (hf == 0) *reinterpret_cast<float4*>(pp + 4 + 4 * d4) = make_float4(a0, a1, a2, a3);
+        __syncwarp();
+        if (lane == 0) { aptx::mbar_arrive(TAIL_FULL(buf)); aptx::mbar_arrive(KV_EMPTY(buf)); }
+      }
+      // ---- epilogue: o = O / l, staged in the tile's (now dead) Q buffer and written by one bulk tensor store
+      const float inv = 1.0f / l;
+      EC_TICK(e0);
+      if (!wait_pv(3u * it + 2u)) goto done;
+      EC_TICK(e1);
       aptx::tc_fence_after();
       uint32_t oa[32], ob[32];
-      uint32_t res[32];
-      aptx::tmem_ld32(tg + 128u, oa);
-      aptx::tmem_ld32(tg + 192u, ob);
-      aptx::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; j += 2)
-        res[j >> 1] = pack_bf16x2(fmaf(__uint_as_float(oa[j]), c0, __uint_as_float(ob[j]) * c1),
-                                  fmaf(__uint_as_float(oa[j + 1]), c0, __uint_as_float(ob[j + 1]) * c1));
-      aptx::tmem_ld32(tg + 160u, oa);
+      aptx::tmem_ld32(tg + 192u, oa);
       aptx::tmem_ld32(tg + 224u, ob);
       aptx::tmem_ld_wait();
       aptx::tc_fence_before();
-      aptx::mbar_arrive(O_FREE(grp));                     // both accumulators are in registers
+      aptx::mbar_arrive(O_FREE(grp));                     // the accumulator is in registers
+      const uint32_t stage = q_smem(grp, buf) + (uint32_t)r * 128u;       // every QK^T of the tile completed before its last P.V
 #pragma unroll
-      for (int j = 0; j < 32; j += 2)
-        res[16 + (j >> 1)] = pack_bf16x2(fmaf(__uint_as_float(oa[j]), c0, __uint_as_float(ob[j]) * c1),
-                                         fmaf(__uint_as_float(oa[j + 1]), c0, __uint_as_float(ob[j + 1]) * c1));
-      bf16* orow = a.out + (size_t)b * a.o_bs + (size_t)(grp * kATile + r) * a.o_rs + (size_t)h * kAD;
+      for (int c = 0; c < 4; ++c)
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)((c ^ (r & 7)) * 16)),
+                     "r"(pack_bf16x2(__uint_as_float(oa[8 * c]) * inv, __uint_as_float(oa[8 * c + 1]) * inv)),
+                     "r"(pack_bf16x2(__uint_as_float(oa[8 * c + 2]) * inv, __uint_as_float(oa[8 * c + 3]) * inv)),
+                     "r"(pack_bf16x2(__uint_as_float(oa[8 * c + 4]) * inv, __uint_as_float(oa[8 * c + 5]) * inv)),
+                     "r"(pack_bf16x2(__uint_as_float(oa[8 * c + 6]) * inv, __uint_as_float(oa[8 * c + 7]) * inv)) : "memory");
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(res[4 * c], res[4 * c + 1], res[4 * c + 2], res[4 * c + 3]);
+      for (int c = 0; c < 4; ++c)
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)(((4 + c) ^ (r & 7)) * 16)),
+                     "r"(pack_bf16x2(__uint_as_float(ob[8 * c]) * inv, __uint_as_float(ob[8 * c + 1]) * inv)),
+                     "r"(pack_bf16x2(__uint_as_float(ob[8 * c + 2]) * inv, __uint_as_float(ob[8 * c + 3]) * inv)),
+                     "r"(pack_bf16x2(__uint_as_float(ob[8 * c + 4]) * inv, __uint_as_float(ob[8 * c + 5]) * inv)),
+                     "r"(pack_bf16x2(__uint_as_float(ob[8 * c + 6]) * inv, __uint_as_float(ob[8 * c + 7]) * inv)) : "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic stores -> the bulk store's async-proxy read
+      aptx::mbar_arrive(OUT_READY(grp));                                 // the group's MMA warp issues the store
+#ifdef EC_ATTN_TIMING
+      { const long long e2 = clock64(); tm_epi_wait += e1 - e0; tm_epi += e2 - e1;
+        const long long* ts = reinterpret_cast<const long long*>(smem_raw + (bar0 + 7168u - smem_u32(smem_raw))) + (grp * 2 + (int)((3u * it + 2u) & 1u)) * 2;
+        tm_h1 += ts[0] - t_arr; tm_h2 += ts[1] - ts[0]; tm_h3 += e1 - ts[1]; }
+#endif
     }
+#ifdef EC_ATTN_TIMING
+    if (blockIdx.x == 3 && lane == 0 && it > 0)
+      printf("attention257 warp %d: %u pairs, per pair: S wait %lld, ld %lld, max+exp %lld, back-pressure %lld, last-PV wait %lld, "
+             "epilogue %lld, total %lld cycles; last P.V: my arrive -> issuer saw P_READY %lld, -> issued %lld, -> I saw PV_DONE %lld\n",
+             warp, it, tm_s / it, tm_ld / it, tm_exp / it, tm_bp / it, tm_epi_wait / it,
+             tm_epi / it, (clock64() - tm_total) / it, tm_h1 / it, tm_h2 / it, tm_h3 / it);
+#endif
   }
 done:
   aptx::tc_fence_before();
@@ -962,13 +1078,15 @@ int attention_sm100_fused_qkv(const bf16* qkv, long long ld, int q_col0, int k_c
   const int grid = std::min(batch * heads, num_sms());
   // 257 tokens (ViT-L/14, ViT-B/16): the block-wise kernel (EC_ATTN_V2=0 or impl 2 of ec_attention_fused_qkv keep v1)
   static const int env_v2 = [] { const char* e = getenv("EC_ATTN_V2"); return e ? atoi(e) : 1; }();
-  if (seq == av2::kSeq && env_v2 != 0 && !force_v1) {
+  if (seq == av2::kSeq && env_v2 != 0 && !force_v1 && o_bs == (long long)seq * o_rs) {     // (one 2-D map covers the output)
     static bool attr2[64] = {};
     if (!attr2[dev_]) {
       EC_CHECK_CUDA(cudaFuncSetAttribute(av2::attention257_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, av2::kSmemBytes));
       attr2[dev_] = true;
     }
-    av2::attention257_kernel<<<grid, av2::kThreads, av2::kSmemBytes, stream>>>(tm128, tm16, a);
+    CUtensorMap tm_out;
+    EC_TRY(encode_map(&tm_out, out, rows, heads * kAD, o_rs, kATile));
+    av2::attention257_kernel<<<grid, av2::kThreads, av2::kSmemBytes, stream>>>(tm128, tm16, tm_out, a);
     EC_POST_LAUNCH();
     return EC_OK;
   }

@@ -156,6 +156,29 @@ def test_attention_tcgen05_fused_qkv(device, B, H, S):
     assert err < 0.03 and rel < 1e-2
 
 
+@pytest.mark.parametrize("first_big", [100, 200, 256])
+def test_attention_tcgen05_257_rescale_path(device, first_big):
+    """The block-wise 257-token kernel keeps block 0's row max as the softmax reference unless a later key block exceeds
+    it by more than 2^8; keys >= `first_big` are scaled up so that (almost) every row takes the rescale path in block 1
+    and / or block 2 (key 256 alone for first_big = 256)."""
+    B, H, S, D = 5, 3, 257, 64
+    C = H * D
+    qkv = _rand_bf16((B, S, 3 * C), device, seed=77).float()
+    qkv[:, first_big:, C:2 * C] *= 9.0
+    qkv = qkv.to(torch.bfloat16)
+    out = ops.attention_fused_qkv(qkv, H, impl=1)
+    ops.check_watchdog(device)
+    qf = qkv[:, :, :C].float().view(B, S, H, D).transpose(1, 2)
+    kf = qkv[:, :, C:2 * C].float().view(B, S, H, D).transpose(1, 2)
+    vf = qkv[:, :, 2 * C:].float().view(B, S, H, D).transpose(1, 2)
+    p = torch.softmax(qf @ kf.transpose(-1, -2) / D ** 0.5, dim=-1)
+    ref = (p @ vf).transpose(1, 2).reshape(B, S, C)
+    err = (out.float() - ref).abs().max().item()
+    rel = ((out.float() - ref).norm() / ref.norm()).item()
+    print(f"257-token attention, keys >= {first_big} x9: max err {err:.4f}, rel {rel:.2e}")
+    assert torch.isfinite(out.float()).all() and err < 0.05 and rel < 1e-2
+
+
 @pytest.mark.parametrize("M,N,K", [(1024, 768, 3072), (300, 768, 768), (20000, 1024, 1024), (33024, 1024, 4096), (129, 512, 256)])
 def test_gemm_fused_layernorm_tail(device, M, N, K):
     """Residual GEMM that also emits LayerNorm(out) as bf16 once a 128-row block is complete (gemm_kernel.cuh::ln_tail):
