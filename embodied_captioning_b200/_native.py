@@ -29,6 +29,7 @@ EXPORTS = [
     "ec_textenc_create", "ec_textenc_destroy", "ec_textenc_set_tensor", "ec_textenc_finalize",
     "ec_textenc_workspace_bytes", "ec_textenc_encode",
     "ec_gemm_bf16_grouped", "ec_gemm_bf16_splitk", "ec_cross_attention_absorbed", "ec_pack_image_tokens", "ec_packed_image_tokens_bytes",
+    "ec_seq_timing_read",
 ]
 
 
@@ -114,6 +115,7 @@ def lib() -> C.CDLL:
     L.ec_launch_count.argtypes = []
     L.ec_launch_count.restype = C.c_int64
     L.ec_profile_gemm.argtypes = [i32]
+    L.ec_seq_timing_read.argtypes = [C.POINTER(C.c_int64), i32]
     L.ec_profile_gemm_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     for name in EXPORTS:
         getattr(L, name)          # AttributeError here means the .so is older than the header: rebuild

@@ -67,6 +67,7 @@ class CoCa(nn.Module):
         self._tc_attention = True
         self._chains = 0
         self._absorbed = os.environ.get("EC_ABSORB", "1") != "0"     # A/B switch for probes
+        self._seq = None                                             # None: the library default (EC_SEQ, on)
         self._dummy = nn.Parameter(torch.zeros(1), requires_grad=False)   # lets `.parameters()` work
 
     # ------------------------------------------------------------------ nn.Module protocol
@@ -129,6 +130,8 @@ class CoCa(nn.Module):
         nat.check(nat.lib().ec_model_set_option(self._handle, b"tc_attention", int(self._tc_attention)))
         nat.check(nat.lib().ec_model_set_option(self._handle, b"decode_chains", self._chains))
         nat.check(nat.lib().ec_model_set_option(self._handle, b"absorbed_cross", int(self._absorbed)))
+        if self._seq is not None:
+            nat.check(nat.lib().ec_model_set_option(self._handle, b"decode_seq", int(self._seq)))
 
     def set_absorbed_cross(self, enabled: bool):
         """Decoder cross-attention in the absorbed-projection form (default) or over per-layer K/V caches; the
@@ -142,6 +145,13 @@ class CoCa(nn.Module):
             if enabled and self._state_dict_ref is not None:
                 self.load_state_dict(self._state_dict_ref)
             self._ws.pop("decode", None)
+
+    def set_decode_seq(self, enabled: bool):
+        """Decoder steps with one persistent GEMM-sequence launch per block, or (default: measured faster) one launch
+        per GEMM / LayerNorm; the results are bit-identical."""
+        self._seq = bool(enabled)
+        if self._handle:
+            nat.check(nat.lib().ec_model_set_option(self._handle, b"decode_seq", int(self._seq)))
 
     def set_decode_graph(self, enabled: bool):
         self._graph = bool(enabled)

@@ -70,6 +70,15 @@ int ec_model_set_option(ec_model* m, const char* key, int value) {
     m->impl.decode_chains = value;
     return EC_OK;
   }
+  if (!strcmp(key, "decode_seq")) {
+    const bool on = value != 0 && m->impl.seq_counters != nullptr;
+    if (on != m->impl.use_seq) {      // another launch set: the captured step graphs are stale
+      for (int c = 0; c < kMaxChains; ++c)
+        if (m->impl.graph_exec[c]) { cudaGraphExecDestroy(m->impl.graph_exec[c]); m->impl.graph_exec[c] = nullptr; }
+    }
+    m->impl.use_seq = on;
+    return EC_OK;
+  }
   if (!strcmp(key, "tc_attention")) { m->impl.use_tc_attention = value != 0; return EC_OK; }
   // takes effect at the next ec_model_finalize (the absorbed weights are built there); switching it off works at once
   if (!strcmp(key, "absorbed_cross")) { m->impl.absorbed_cross = value != 0; return EC_OK; }
@@ -316,6 +325,10 @@ int ec_profile_gemm_read(double* ms, double* flops, int64_t* launches) {
   EC_TRY(gemm_profile_read(ms, flops, &l));
   if (launches) *launches = l;
   return EC_OK;
+}
+
+int ec_seq_timing_read(int64_t* out_host, int32_t count) {
+  return gemm_seq_timing_read(reinterpret_cast<long long*>(out_host), count);
 }
 
 }  // extern "C"

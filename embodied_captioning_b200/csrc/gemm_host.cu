@@ -1,7 +1,9 @@
 // Host side of the tcgen05 GEMM: tensor maps, tile-shape heuristic, launch, profiling hooks, SIMT cross-check.
 #include "gemm_kernel.cuh"
+#include "gemm_seq.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -302,6 +304,113 @@ static int gemm_dispatch(const GemmArgs& a, GemmEpilogue epi, cudaStream_t strea
   }
   set_error("unknown GEMM epilogue %d", (int)epi);
   return EC_ERR_INVALID;
+}
+
+// ============================================================================================
+// GEMM sequence (gemm_seq.cuh)
+// ============================================================================================
+static_assert(kGemmSeqMaxStages == kSeqMaxStages && kGemmSeqCounterInts == kSeqCounterInts, "gemm_seq constants");
+
+// tile width the stand-alone dispatch (launch_epi) would give this stage on the 1-CTA kernel; -1: not a sequence stage
+static int seq_stage_bn(const GemmArgs& a, GemmEpilogue epi) {
+  if (epi != EPI_BF16 && epi != EPI_BF16_GELU && epi != EPI_F32_RESID) return -1;
+  if (a.split_k > 1 || a.M <= 0 || a.N <= 0 || a.K <= 0 || a.N % 8 != 0) return -1;
+  if (a.group_cols > 0) {
+    if (epi != EPI_BF16 || a.N % a.group_cols != 0 || a.K % kBK != 0 || a.group_cols % 64 != 0) return -1;
+    int bn = a.bn_hint;
+    if (bn == 0) bn = (a.group_cols % 256 == 0) ? 256 : (a.group_cols % 128 == 0 ? 128 : 64);
+    return (a.group_cols % bn == 0 && (bn == 64 || bn == 128 || bn == 256)) ? bn : -1;
+  }
+  if (pair_shape(a.M, a.N)) return -1;
+  const int sms = num_sms(), tm = ceil_div(a.M, kBM);
+  if (epi != EPI_F32_RESID) {
+    const int t128 = tm * ceil_div(a.N, 128), t192 = tm * ceil_div(a.N, 192);
+    if (a.N % 192 == 0 && t128 > sms && t192 <= sms) return 192;
+  }
+  if (tm * ceil_div(a.N, 256) >= sms) return epi == EPI_F32_RESID ? -1 : 256;
+  if (tm * ceil_div(a.N, 128) >= sms / 2 || a.N >= 1024) return 128;
+  return 64;
+}
+
+bool gemm_seq_supported(const GemmSeqStage* st, int n) {
+  if (st == nullptr || n < 1 || n > kSeqMaxStages) return false;
+  const int M = st[0].a.M;
+  if (M < 1 || ceil_div(M, kBM) > kSeqMaxRowBlocks) return false;
+  for (int i = 0; i < n; ++i) {
+    const GemmArgs& a = st[i].a;
+    const int bn = seq_stage_bn(a, st[i].epi);
+    if (bn < 0 || a.M != M || !a.A || !a.W || !a.out) return false;
+    if (a.lda % 8 != 0 || a.ldw % 8 != 0 || a.ldo % 8 != 0) return false;
+    if (st[i].epi == EPI_F32_RESID && (a.residual == nullptr || a.ldr % 4 != 0)) return false;
+    if (a.ln_out != nullptr) {
+      if (st[i].epi != EPI_F32_RESID || !a.ln_gamma || !a.ln_beta || a.N % 4 != 0 || a.N > kLnTailMaxVec * 128 || a.ld_ln % 4 != 0)
+        return false;
+      // the tail waits inside the epilogue for the block's other n-tiles: they must all be resident at once
+      if (ceil_div(M, kBM) * ceil_div(a.N, bn) > num_sms()) return false;
+    }
+  }
+  return true;
+}
+
+int gemm_seq_timing_read(long long* host, int count) {
+  const size_t total = (size_t)kSeqTimingTags * kSeqMaxStages * kSeqTimingEvents;
+  EC_REQUIRE(host != nullptr && count > 0 && (size_t)count <= total, EC_ERR_INVALID, "gemm_seq_timing_read: bad arguments");
+  EC_CHECK_CUDA(cudaDeviceSynchronize());
+  EC_CHECK_CUDA(cudaMemcpyFromSymbol(host, g_seq_timing, (size_t)count * sizeof(long long)));
+  return EC_OK;
+}
+
+int gemm_seq(const GemmSeqStage* st, int n, int* counters, const int* skip_flag, const void* prefetch_ptr,
+             size_t prefetch_bytes, cudaStream_t stream, int timing_tag) {
+  EC_REQUIRE(gemm_seq_supported(st, n), EC_ERR_UNSUPPORTED, "GEMM sequence: unsupported stage list");
+  EC_REQUIRE(counters != nullptr, EC_ERR_INVALID, "GEMM sequence: null counters");
+  SeqMaps maps;
+  SeqParams cp;
+  memset(&maps, 0, sizeof(maps));
+  memset(&cp, 0, sizeof(cp));
+  const int M = st[0].a.M;
+  cp.n_stages = n; cp.tiles_m = ceil_div(M, kBM); cp.counters = counters; cp.skip_flag = skip_flag;
+  cp.pf_ptr = reinterpret_cast<const unsigned char*>(prefetch_ptr); cp.pf_bytes = prefetch_bytes;
+  cp.tag = timing_tag;
+  int max_tiles = 1;
+  for (int i = 0; i < n; ++i) {
+    const GemmArgs& a = st[i].a;
+    const int bn = seq_stage_bn(a, st[i].epi);
+    const int groups = a.group_cols > 0 ? a.N / a.group_cols : 1;
+    EC_REQUIRE(a.lda >= a.K * groups && a.ldw >= a.K, EC_ERR_INVALID, "GEMM sequence: row strides shorter than K");
+    EC_TRY(make_tmap(&maps.a[i], a.A, a.M, a.K * groups, a.lda, kBM));
+    EC_TRY(make_tmap(&maps.w[i], a.W, a.N, a.K, a.ldw, bn));
+    SeqStageDev& d = cp.st[i];
+    EpiParams& p = d.p;
+    p.M = a.M; p.N = a.N; p.bias = a.bias; p.residual = a.residual; p.ldr = a.ldr; p.out = a.out; p.ldo = a.ldo;
+    p.eos_col = -1; p.split_k = 1; p.grp_cols = a.group_cols;
+    p.ln_g = a.ln_gamma; p.ln_b = a.ln_beta; p.ln_out = a.ln_out; p.ld_ln = a.ld_ln;
+    p.pf_ptr = reinterpret_cast<const unsigned char*>(a.W);            // warp 2 pulls the later stages' weights into L2
+    p.pf_bytes = (unsigned long long)a.N * a.ldw * sizeof(bf16);
+    d.K = a.K; d.bn = bn; d.epi = (int)st[i].epi; d.tiles_n = ceil_div(a.N, bn);
+    d.ln_tail = a.ln_out != nullptr ? 1 : 0;
+    d.dep = 0;
+    if (i > 0) {
+      const GemmArgs& prev = st[i - 1].a;
+      if (prev.ln_out != nullptr && a.A == prev.ln_out) d.dep = 2;
+      else if (a.A == reinterpret_cast<const bf16*>(prev.out)) d.dep = 1;
+      // the residual stream of a later stage is complete only when the stage before it has stored the whole row block
+      else if (st[i].epi == EPI_F32_RESID) d.dep = 1;
+    }
+    max_tiles = std::max(max_tiles, cp.tiles_m * d.tiles_n);
+  }
+  const int grid = std::min(max_tiles, num_sms());
+  static bool attr_done[64] = {};
+  const int dev_ = current_device();
+  EC_REQUIRE(dev_ >= 0 && dev_ < 64, EC_ERR_DEVICE, "no current CUDA device");
+  if (!attr_done[dev_]) {
+    EC_CHECK_CUDA(cudaFuncSetAttribute(gemm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmemBytes));
+    attr_done[dev_] = true;
+  }
+  note_launches(1);
+  // no programmatic dependent launch: the kernel has no griddepcontrol.wait
+  EC_CHECK_CUDA(launch_kernel_pdl(false, gemm_seq_kernel, dim3(grid), dim3(kThreads1), (size_t)kSeqSmemBytes, stream, maps, cp));
+  return EC_OK;
 }
 
 int gemm_check_watchdog(cudaStream_t stream) {

@@ -65,6 +65,19 @@ int gemm_argmax_parts(int N);
 // Launch. Returns EC_OK or an error code (set_error() filled in).
 int gemm_bf16(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream);
 
+// ---- GEMM sequence (gemm_seq.cuh): up to kGemmSeqMaxStages small dependent GEMMs, each reading the rows the one
+// before it (or its LayerNorm tail: a.ln_out != nullptr, EPI_F32_RESID) produced, as ONE persistent launch.  Stage
+// shapes are those of the 1-CTA kernel; results are bit-identical to launching the stages one after the other.
+// `counters`: kGemmSeqCounterInts ints, ZERO at launch.  gemm_seq_supported() says whether a list can run fused.
+struct GemmSeqStage { GemmArgs a; GemmEpilogue epi; };
+constexpr int kGemmSeqMaxStages = 6;
+constexpr int kGemmSeqCounterInts = kGemmSeqMaxStages * 2 * 16 * 32;      // one 128-byte line per counter
+bool gemm_seq_supported(const GemmSeqStage* st, int n);
+int gemm_seq(const GemmSeqStage* st, int n, int* counters, const int* skip_flag, const void* prefetch_ptr,
+             size_t prefetch_bytes, cudaStream_t stream, int timing_tag = -1);
+// stage clocks of CTA 0 recorded by -DEC_SEQ_TIMING builds: [64 tags][6 stages][16 events] cycles (zeros otherwise)
+int gemm_seq_timing_read(long long* host, int count);
+
 // Test / debug helper: plain SIMT reference GEMM with the same epilogues (used by the unit tests to
 // cross-check the tensor-core kernel on device; never called by the model path).
 int gemm_reference_simt(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream);

@@ -77,6 +77,20 @@ Model::Model(const ec_config& c, int dev) : cfg(c), device(dev) {
   // 128-row block (latency-bound row loop on the GEMM's critical path) where the stand-alone kernel spreads the rows
   // over every SM at the HBM roofline, and every tile pays two named barriers + a device-scope fence + an atomic.
   // Encoder 180 -> 220 ms, decoder 113 -> 150 ms at 1024 crops.  Opt-in only (EC_FUSE_LN=1).
+  const size_t n_seq = (size_t)kMaxChains * kSeqLaunchesPerStep * kGemmSeqCounterInts;
+  if (cudaMalloc(&seq_counters, n_seq * sizeof(int)) == cudaSuccess) {
+    cudaMemset(seq_counters, 0, n_seq * sizeof(int));
+    owned.push_back(seq_counters);
+  } else {
+    seq_counters = nullptr;
+  }
+  // Measured on B200 at 1024 crops (profiles/r02_gemm_seq.txt): bit-identical, ~80 graph nodes per step instead of ~280,
+  // and SLOWER -- decoder alone 94.6 vs 86.6 ms, inside the bench loop 115.7 vs 109.5.  The hand-over itself is cheap
+  // (0.4-1.1 us from "rows published" to the next stage's first operands), but publishing a tile costs the epilogue
+  // + a GPU-scope release (2.3-3 us per tile), the LayerNorm tail 4-5 us against 3.65 us for the stand-alone launch,
+  // and a lone CTA's GELU epilogue is 5 us either way.  Opt-in (EC_SEQ=1 / option "decode_seq").
+  static const int env_seq = [] { const char* e = getenv("EC_SEQ"); return e ? atoi(e) : 0; }();
+  use_seq = env_seq != 0 && seq_counters != nullptr;
   static const int env_pf = [] { const char* e = getenv("EC_PREFETCH_WEIGHTS"); return e ? atoi(e) : 1; }();
   prefetch_weights = env_pf != 0;
   static const int env_lnkv = [] { const char* e = getenv("EC_SHARED_LNKV"); return e ? atoi(e) : 1; }();
@@ -457,6 +471,7 @@ struct DecodeWs {
   float* part_val; int* part_idx; unsigned char* finished; DecodeState* st; int* tokens_tf;
   int* ln_cnt;           // fused-LayerNorm row-block counters of this chain
   float* sk_ws; int* sk_cnt;   // split-K partial tiles ([3][n][T] floats) and tile counters of this chain's FC2 GEMMs
+  int* seq_cnt;          // GEMM-sequence counters of this chain (kSeqLaunchesPerStep x kGemmSeqCounterInts)
   size_t cache_layer;    // elements between the self-K/V caches of consecutive layers (whole batch)
   size_t cross_layer;    // elements between the cross-K/V caches of consecutive layers (whole batch)
   size_t bytes;
@@ -478,6 +493,7 @@ static DecodeWs slice_rows(const Model& m, const DecodeWs& w, int r0, int seq_le
   v.ln_cnt = m.ln_counters + kLnCountersEncoder + chain * kLnCountersPerChain;
   v.sk_ws += r * 3 * T;
   v.sk_cnt = m.sk_counters ? m.sk_counters + chain * kSkCountersPerChain : nullptr;
+  v.seq_cnt = m.seq_counters ? m.seq_counters + (size_t)chain * kSeqLaunchesPerStep * kGemmSeqCounterInts : nullptr;
   return v;
 }
 
@@ -511,6 +527,7 @@ static DecodeWs carve_decode(const Model& m, void* ws, int n, int seq_len) {
   w.sk_ws = b.take<float>((size_t)n * 3 * T);
   w.sk_cnt = m.sk_counters;
   w.ln_cnt = m.ln_counters + kLnCountersEncoder;
+  w.seq_cnt = m.seq_counters;
   w.cache_layer = (size_t)n * L * T;
   w.cross_layer = (size_t)n * NK * 2 * T;
   w.bytes = b.off;
@@ -591,7 +608,9 @@ int Model::cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int la
 // token cur_len out.  Chains only share the read-only step state and the `next_active` counter.
 int Model::chain_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len,
                       float* logits, bool teacher_forced, cudaStream_t s) {
-  const int T = cfg.text_width, V = cfg.vocab_size;
+  if (use_seq && w.seq_cnt != nullptr && cfg.text_layers + cfg.mm_layers > 0 && !decoder_fuse(n))
+    return chain_step_seq(w, tokens, ld_tokens, n, n_total, seq_len, min_len, logits, teacher_forced, s);
+  const int T = cfg.text_width;
   EC_TRY(decode_embed(tokens, ld_tokens, tok_emb, txt_pos, w.x, n, T, w.st, s));
   // block sequence: text tower, then (self, cross) pairs, then ln_final; each block's c_proj GEMM also produces the
   // LayerNorm the NEXT block starts with (fused tail), so only the very first LayerNorm of the step is a launch
@@ -615,6 +634,13 @@ int Model::chain_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int 
                        s));
   }
   if (!fuse) EC_TRY(layernorm(w.x, T, ln_final_g, ln_final_b, w.ln, T, true, n, T, &w.st->done, s));
+  return vocab_head(w, tokens, ld_tokens, n, n_total, seq_len, min_len, logits, teacher_forced, s);
+}
+
+// vocabulary projection of ln_final(x) (in w.ln) with the arg-max epilogue, then the token selection
+int Model::vocab_head(const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len,
+                      float* logits, bool teacher_forced, cudaStream_t s) {
+  const int T = cfg.text_width, V = cfg.vocab_size;
   GemmArgs g{};
   g.A = w.ln; g.lda = T; g.W = w_vocab; g.ldw = T; g.M = n; g.N = V; g.K = T;
   g.logits = logits; g.ld_logits = V; g.logits_step_stride = (long long)n_total * V;
@@ -626,6 +652,118 @@ int Model::chain_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int 
     EC_TRY(decode_select(w.part_val, w.part_idx, g.n_parts, tokens, ld_tokens, w.finished, n, seq_len,
                          cfg.eos_token_id, cfg.pad_token_id, w.st, s));
   return EC_OK;
+}
+
+// A list of dependent GEMM stages (+ LayerNorm tails): one persistent launch when the shapes allow it, else the stages
+// one after the other with stand-alone LayerNorms (same arithmetic, same results).
+int Model::run_stages(const GemmSeqStage* st, int ns, int* counters, const int* skip, Prefetch pf, int n, cudaStream_t s,
+                      int tag) {
+  static const int env_max = [] { const char* e = getenv("EC_SEQ_MAX"); return e ? atoi(e) : 0; }();   // probe: stages per launch
+  if (counters != nullptr && gemm_seq_supported(st, ns)) {
+    if (env_max > 0 && env_max < ns) {
+      // every group needs its own zeroed counter block: groups of one launch share `counters` at stage offsets
+      for (int i = 0; i < ns; i += env_max) {
+        const int cnt = std::min(env_max, ns - i);
+        EC_TRY(gemm_seq(st + i, cnt, counters + (size_t)i * (kGemmSeqCounterInts / kGemmSeqMaxStages), skip, nullptr, 0, s,
+                        i == 0 ? tag : -1));
+      }
+      return EC_OK;
+    }
+    return gemm_seq(st, ns, counters, skip, prefetch_weights ? pf.ptr : nullptr, prefetch_weights ? pf.bytes : 0, s, tag);
+  }
+  for (int i = 0; i < ns; ++i) {
+    GemmArgs a = st[i].a;
+    const float* g = a.ln_gamma; const float* b = a.ln_beta; bf16* lo = a.ln_out; const int ld = a.ld_ln;
+    a.ln_gamma = a.ln_beta = nullptr; a.ln_out = nullptr; a.ld_ln = 0;
+    a.skip_flag = skip;
+    EC_TRY(gemm_bf16(a, st[i].epi, s));
+    if (lo != nullptr)
+      EC_TRY(layernorm(reinterpret_cast<const float*>(a.out), a.ldo, g, b, lo, ld, true, n, a.N, skip, s));
+  }
+  return EC_OK;
+}
+
+// The decoder step with GEMM sequences: per block one attention kernel and ONE persistent launch for everything up to
+// the next attention -- [V-projection of the absorbed contexts] -> out_proj (+x) -> ln_2 -> FC1 + GELU -> FC2 (+x) ->
+// the next block's ln_1 -> its QKV (self) or Q + absorbed Q' (cross).  ~80 graph nodes per step instead of ~280.
+int Model::chain_step_seq(const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len,
+                          float* logits, bool teacher_forced, cudaStream_t s) {
+  const int T = cfg.text_width, NK = cfg.n_queries - 1;
+  const int* skip = &w.st->done;
+  struct Blk { const Block* b; int cross; int layer; bf16* kc; bf16* vc; int heads; };
+  std::vector<Blk> blks;
+  for (int l = 0; l < cfg.text_layers; ++l)
+    blks.push_back(Blk{&tblocks[l], 0, l, w.tk + l * w.cache_layer, w.tv + l * w.cache_layer, cfg.text_heads});
+  for (int l = 0; l < cfg.mm_layers; ++l) {
+    blks.push_back(Blk{&dself[l], 0, l, w.dk + l * w.cache_layer, w.dv + l * w.cache_layer, cfg.mm_heads});
+    blks.push_back(Blk{&dcross[l], 1, l, nullptr, nullptr, cfg.mm_heads});
+  }
+  const int nb = (int)blks.size();
+  EC_REQUIRE(nb > 0 && nb <= kSeqLaunchesPerStep && blks[0].cross == 0, EC_ERR_UNSUPPORTED, "decoder without blocks");
+  const bool absorbed = use_absorbed();
+  const int H = cfg.mm_heads, hd = T / H;
+  const size_t TTb = (size_t)T * T * sizeof(bf16);
+
+  EC_TRY(decode_embed(tokens, ld_tokens, tok_emb, txt_pos, w.x, n, T, w.st, s));
+  EC_CHECK_CUDA(cudaMemsetAsync(w.seq_cnt, 0, (size_t)nb * kGemmSeqCounterInts * sizeof(int), s));
+  EC_TRY(layernorm(w.x, T, blks[0].b->ln1_g, blks[0].b->ln1_b, w.ln, T, true, n, T, skip, s));
+  EC_TRY(linear(w.ln, T, blks[0].b->w_qkv, T, blks[0].b->b_qkv, n, 3 * T, T, w.qkv, 3 * T, EPI_BF16, nullptr, 0, skip, s,
+                nullptr, prefetch_weights ? Prefetch{blks[0].b->w_out, TTb} : Prefetch()));
+
+  auto stage = [&](const bf16* A, int lda, const bf16* W, int ldw, const float* bias, int N, int K, void* out, int ldo,
+                   GemmEpilogue epi) {
+    GemmSeqStage st{};
+    st.a.A = A; st.a.lda = lda; st.a.W = W; st.a.ldw = ldw; st.a.bias = bias; st.a.M = n; st.a.N = N; st.a.K = K;
+    st.a.out = out; st.a.ldo = ldo; st.epi = epi;
+    if (epi == EPI_F32_RESID) { st.a.residual = reinterpret_cast<const float*>(out); st.a.ldr = ldo; }
+    return st;
+  };
+  for (int i = 0; i < nb; ++i) {
+    const Blk& k = blks[i];
+    const Block& b = *k.b;
+    GemmSeqStage st[kGemmSeqMaxStages];
+    int ns = 0;
+    if (!k.cross) {
+      EC_TRY(decode_self_attention(w.qkv, k.kc, k.vc, w.att, n, k.heads, T / k.heads, seq_len, w.finished, w.st, s));
+    } else if (absorbed) {
+      static const int env_rev = [] { const char* e = getenv("EC_XA_REVERSE"); return e ? atoi(e) : 1; }();
+      EC_TRY(decode_cross_absorbed(w.qp, w.ln_kv, w.ctx, n, H, T, NK, w.finished, w.st, env_rev != 0 && (k.layer & 1), s));
+      st[ns] = stage(w.ctx, H * T, wkv_fold[k.layer] + (size_t)T * T, T, bkv_fold[k.layer] + T, T, T, w.att, T, EPI_BF16);
+      st[ns].a.group_cols = hd; st[ns].a.bn_hint = 64;
+      ++ns;
+    } else {
+      EC_TRY(decode_cross_attention(w.q, w.cross_kv + k.layer * w.cross_layer, w.att, n, H, hd, NK, w.finished, w.st, s));
+    }
+    st[ns] = stage(w.att, T, b.w_out, T, b.b_out, T, T, w.x, T, EPI_F32_RESID);
+    st[ns].a.ln_gamma = b.ln2_g; st[ns].a.ln_beta = b.ln2_b; st[ns].a.ln_out = w.ln; st[ns].a.ld_ln = T;
+    ++ns;
+    st[ns++] = stage(w.ln, T, b.w_fc1, T, b.b_fc1, 4 * T, T, w.fc1, 4 * T, EPI_BF16_GELU);
+    st[ns] = stage(w.fc1, 4 * T, b.w_fc2, 4 * T, b.b_fc2, T, 4 * T, w.x, T, EPI_F32_RESID);
+    const bool last = (i + 1 == nb);
+    const Block* nxt = last ? nullptr : blks[i + 1].b;
+    st[ns].a.ln_gamma = last ? ln_final_g : nxt->ln1_g; st[ns].a.ln_beta = last ? ln_final_b : nxt->ln1_b;
+    st[ns].a.ln_out = w.ln; st[ns].a.ld_ln = T;
+    ++ns;
+    Prefetch pf;
+    if (!last) {
+      const Blk& kn = blks[i + 1];
+      if (!kn.cross) {
+        st[ns++] = stage(w.ln, T, nxt->w_qkv, T, nxt->b_qkv, 3 * T, T, w.qkv, 3 * T, EPI_BF16);
+      } else {
+        st[ns++] = stage(w.ln, T, nxt->w_qkv, T, nxt->b_qkv, T, T, w.q, T, EPI_BF16);      // q rows only
+        if (absorbed) {
+          st[ns] = stage(w.q, T, wk_abs[kn.layer], hd, nullptr, H * T, hd, w.qp, H * T, EPI_BF16);
+          st[ns].a.group_cols = T;
+          ++ns;
+        }
+      }
+      pf = Prefetch{nxt->w_out, TTb};       // the first weights of the next sequence
+    } else {
+      pf = Prefetch{blks[0].b->w_qkv, 3 * TTb};
+    }
+    EC_TRY(run_stages(st, ns, w.seq_cnt ? w.seq_cnt + (size_t)i * kGemmSeqCounterInts : nullptr, skip, pf, n, s, i));
+  }
+  return vocab_head(w, tokens, ld_tokens, n, n_total, seq_len, min_len, logits, teacher_forced, s);
 }
 
 // Rows per chain.  The batch can be cut into independent row chains; each chain owns a stream, a device-resident

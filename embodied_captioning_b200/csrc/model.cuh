@@ -23,6 +23,7 @@ constexpr int kMaxChains = 8;
 constexpr int kLnCountersEncoder = 4096;     // 128-row blocks of one image-tower call (1024 crops x 257 tokens = 2056)
 constexpr int kLnCountersPerChain = 64;      // 128-row blocks of one decoder chain
 constexpr int kSkCountersPerChain = 256;     // output tiles of one split-K GEMM of a decoder chain
+constexpr int kSeqLaunchesPerStep = 64;      // GEMM-sequence launches of one decoder step (one per block), per chain
 
 struct Model {
   ec_config cfg;
@@ -46,6 +47,10 @@ struct Model {
   float *unit_gamma = nullptr, *zero_beta = nullptr;
   int* ln_counters = nullptr;      // row-block arrival counters of the fused tails (zero between launches)
   int* sk_counters = nullptr;      // split-K tile counters of the decoder's FC2 GEMMs, kSkCountersPerChain per chain
+  // decoder steps: the GEMMs + LayerNorms between two attention kernels as ONE persistent launch (gemm_seq.cuh; option
+  // "decode_seq" / EC_SEQ=1; default OFF: bit-identical but measured slower, profiles/r02_gemm_seq.txt)
+  bool use_seq = false;
+  int* seq_counters = nullptr;     // kMaxChains x kSeqLaunchesPerStep x kGemmSeqCounterInts, zeroed at the top of every step
   bool use_tc_attention = false;   // tcgen05/TMEM attention for the ViT blocks (option "tc_attention")
   int patch_k = 0, patch_ld = 0;
 
@@ -105,6 +110,12 @@ struct Model {
   int chain_rows(int n) const;
   int chain_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len,
                  float* logits, bool teacher_forced, cudaStream_t s);
+  int chain_step_seq(const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len,
+                     float* logits, bool teacher_forced, cudaStream_t s);
+  int run_stages(const GemmSeqStage* st, int ns, int* counters, const int* skip, Prefetch pf, int n, cudaStream_t s,
+                 int tag = -1);
+  int vocab_head(const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len, float* logits,
+                 bool teacher_forced, cudaStream_t s);
   int decode_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len,
                   float* logits, bool teacher_forced, cudaStream_t s);
   int run_chain(int c, const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len,

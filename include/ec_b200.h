@@ -206,6 +206,9 @@ int ec_check_watchdog(void* stream);   /* EC_ERR_TIMEOUT if a tcgen05 / bulk-cop
 int64_t ec_launch_count(void);          /* kernels launched by this library so far (graph replays included) */
 int ec_profile_gemm(int32_t enable);    /* time every non-captured tcgen05 GEMM launch with CUDA events */
 int ec_profile_gemm_read(double* ms, double* flops, int64_t* launches);   /* sums since the last read; resets */
+/* Stage clocks of the decoder's GEMM-sequence kernel (csrc/gemm_seq.cuh), recorded by CTA 0 in builds with
+ * -DEC_SEQ_TIMING (zeros otherwise): [64 launches of a step][6 stages][16 events] SM cycles since kernel entry. */
+int ec_seq_timing_read(int64_t* out_host, int32_t count);
 
 #ifdef __cplusplus
 }

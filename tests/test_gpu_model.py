@@ -350,3 +350,36 @@ def test_absorbed_cross_attention_agrees_with_kv_cache_path(device, name):
     print(f"{name}: logits rel err vs oracle: absorbed {rel_ab:.2e}, K/V cache {rel_kv:.2e}; absorbed vs K/V {rel:.2e}")
     assert rel_ab < 3e-2 and rel_kv < 3e-2 and rel < 3e-2
     assert rel_ab < 2.0 * rel_kv + 1e-3          # the absorbed form must not be a worse approximation of fp32
+
+
+@pytest.mark.parametrize("name,n,absorbed,graph", [("coca_tiny", 37, True, False), ("coca_small", 150, True, True),
+                                                    ("coca_small", 300, False, True), ("coca_ViT-B-32", 129, True, True)])
+def test_gemm_sequence_step_is_bit_identical_to_separate_launches(device, name, n, absorbed, graph):
+    """Decoder steps with ONE persistent GEMM-sequence launch per block (csrc/gemm_seq.cuh: out_proj -> ln_2 -> FC1 ->
+    FC2 -> next ln_1 -> next QKV / Q, handed over through per-row-block counters) vs one launch per GEMM and per
+    LayerNorm: the same tiles, the same k-block order, the same LayerNorm arithmetic -> identical logits and tokens."""
+    cfg = get_config(name)
+    sd = synth.make_state_dict(cfg, seed=5)
+    g = torch.Generator().manual_seed(21)
+    t = 7
+    embs = torch.randn((n, cfg.n_image_embs, cfg.embed_dim), generator=g).to(device)
+    text = torch.randint(1, cfg.vocab_size - 2, (n, t), generator=g).to(device)
+    res = []
+    for seq in (True, False):
+        model = CoCa(cfg, device=device)
+        model._absorbed = absorbed
+        model.load_state_dict(sd)
+        model.set_decode_graph(graph)
+        model.set_decode_seq(seq)
+        logits = model.forward(None, text, image_latent=torch.zeros(n, cfg.embed_dim), image_embs=embs,
+                               output_labels=False)["logits"]
+        tok = model.generate(None, image_embs=embs, generation_type="top_k", seq_len=12, fixed_output_length=True,
+                             return_logits=False)["text"]
+        tok2 = model.generate(None, image_embs=embs, generation_type="top_k", seq_len=12, fixed_output_length=True,
+                              return_logits=False)["text"]           # graph replay with re-zeroed counters
+        ops.check_watchdog(device)
+        assert torch.equal(tok, tok2)
+        res.append((logits.cpu(), tok.cpu()))
+    assert torch.isfinite(res[0][0]).all()
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][1], res[1][1])
