@@ -51,8 +51,10 @@ constexpr int kNS = 96 / kKC;    // ring depth (chunks): the ring holds 96 keys,
 constexpr int kKPT = kKC / 8;    // keys per softmax thread
 constexpr int kPrefetch = 0;     // L2 prefetch ahead of the ring: measured WORSE (125 vs 92 us, 667 vs 426 MB of DRAM reads)
 constexpr int kGroupWarps = 8;   // warps of the score group; the context group has as many
-constexpr int kSoftWarps = 4;    // softmax group: 16 rows x 8 threads, 4 keys of the chunk per thread
-constexpr int kThreads = (2 * kGroupWarps + kSoftWarps + 1) * 32;     // + the producer warp
+// softmax group: SW warps = 4 SW rows x 8 threads, 4 keys of the chunk per thread.  SW = 3 serves up to 12 heads (every
+// CoCa decoder) with 20 warps per CTA = 5 per scheduler, which lifts the register cap from 80 to 96 per thread: the
+// context warps then keep several LDSM.T quads in flight instead of serialising LDSM.T -> 2 HMMA through one quad.
+template <int SW> constexpr int kThreadsOf = (2 * kGroupWarps + SW + 1) * 32;     // + the producer warp
 constexpr int kSpLd = kKC + 8;   // floats per row of a partial-score tile (+ 8 pad: conflict-free float2 stores)
 constexpr int kPLd = kKC + 8;    // bf16 per row of the probability tile (conflict-free ldmatrix)
 
@@ -70,7 +72,7 @@ template <int T> struct Cfg {
   static constexpr int kSmem = kNS * kStageBytes + kQBytes + kSpBytes + kPBytes + kStatBytes + kBarBytes + 128;
   static_assert(kSmem <= 227 * 1024, "shared memory budget exceeded");
   static_assert(T % (kGroupWarps * 16) == 0, "feature width must split into 16-wide k-steps per warp");
-  static_assert(kSoftWarps * 32 == 16 * 8 && (kKC == 32 || kKC == 16), "the softmax maps 128 threads onto 16 rows x 8 key groups");
+  static_assert(kKC == 32 || kKC == 16, "the softmax maps 8 threads onto the keys of a chunk");
 };
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -104,6 +106,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// the same copy with an L2 eviction policy (createpolicy): the image tokens are a 0.4 GB stream that is read once per
+// launch -- evict-first keeps it from flushing the step's small hot data (kernel parameters, tensor maps, biases,
+// activations, code) out of the 126 MB L2
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -123,8 +137,8 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <int T>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int T, int SW>
+__global__ void __launch_bounds__(kThreadsOf<SW>, 1)
 cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, bf16* __restrict__ ctx, int n, int heads,
                       int n_kv, const unsigned char* __restrict__ finished, const DecodeState* __restrict__ st, int reverse) {
   using C = Cfg<T>;
@@ -162,7 +176,7 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
   // Traversal order.  The image tokens are the same tensor for every layer, and what the previous layer's launch read
   // last is still in L2 (126 MB of the 0.4 GB): odd layers walk the crops backwards (`reverse`), so that every launch
   // starts on the part of the tensor the one before it finished on.  `b` below is a position in the walk.
-  auto crop_of = [&](int b) { return reverse ? n - 1 - b : b; };
+  auto crop_of = [&](int b) { return (reverse & 1) ? n - 1 - b : b; };
   auto next_active = [&](int b) {
     if (finished != nullptr)
       while (b < n && finished[crop_of(b)]) b += (int)gridDim.x;
@@ -187,7 +201,7 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
   }
   {
     uint4* z = reinterpret_cast<uint4*>(gen + kNS * C::kStageBytes);
-    for (int i = tid; i < C::kQBytes / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < C::kQBytes / 16; i += kThreadsOf<SW>) z[i] = make_uint4(0, 0, 0, 0);
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic zero-fill before the async-proxy copies
   __syncthreads();
@@ -198,12 +212,15 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
   // NOTE on the `__threadfence_block()` before every consumer-side mbarrier arrive: ptxas schedules the SYNCS.ARRIVE
   // above the warp's last LDSM / HMMA instructions otherwise (seen in the SASS), and the stage was then refilled while
   // it was still being read -- about one corrupted crop in 300 on B200.
+  constexpr int kSoftWarps = SW;
   if (warp == 2 * kGroupWarps + kSoftWarps) {
     // =============================================================== producer warp: one bulk copy per chunk / per Q'.
     // The ring holds two chunks in flight (~97 KB per SM, 14 MB on the chip) -- not enough to cover the HBM latency at
     // full bandwidth -- so the chunks further ahead are pulled into L2 first (cp.async.bulk.prefetch.L2, kPrefetch
     // chunks ahead of the copy cursor, across crop boundaries): the copies into shared memory then hit L2.
     int gi = 0;
+    const bool evict_first = (reverse & 2) != 0;
+    const uint64_t policy = policy_evict_first();
     int pf_crop = first, pf_chunk = 0;
     auto prefetch_next = [&]() {
       if (pf_crop >= n) return;
@@ -218,7 +235,8 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
       if (lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(qfull_bar, (uint32_t)heads * (uint32_t)C::kQRowBytes);
-        bulk_g2s(qs, qp + (size_t)crop_of(cb) * heads * T, (uint32_t)heads * (uint32_t)C::kQRowBytes, qfull_bar);
+        if (evict_first) bulk_g2s_hint(qs, qp + (size_t)crop_of(cb) * heads * T, (uint32_t)heads * (uint32_t)C::kQRowBytes, qfull_bar, policy);
+        else bulk_g2s(qs, qp + (size_t)crop_of(cb) * heads * T, (uint32_t)heads * (uint32_t)C::kQRowBytes, qfull_bar);
       }
       for (int c = 0; c < nchunks; ++c, ++gi) {
         const int stage = gi % kNS;
@@ -227,9 +245,9 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
         if (lane == 0) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // consumers' generic-proxy reads -> async-proxy write
           mbar_expect_tx(full_bar(stage), (uint32_t)C::kStageBytes);
-          bulk_g2s(stage0 + stage * C::kStageBytes,
-                   reinterpret_cast<const uint8_t*>(xn) + ((size_t)crop_of(cb) * nchunks + c) * C::kStageBytes,
-                   (uint32_t)C::kStageBytes, full_bar(stage));
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(xn) + ((size_t)crop_of(cb) * nchunks + c) * C::kStageBytes;
+          if (evict_first) bulk_g2s_hint(stage0 + stage * C::kStageBytes, src, (uint32_t)C::kStageBytes, full_bar(stage), policy);
+          else bulk_g2s(stage0 + stage * C::kStageBytes, src, (uint32_t)C::kStageBytes, full_bar(stage));
         }
         __syncwarp();
       }
@@ -383,7 +401,7 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
         }
         if (c8 == 0) { stat[buf * 16 + r] = corr; stat[32 + buf * 16 + r] = l_run; }
         __threadfence_block();
-        asm volatile("bar.sync 1, %0;" ::"n"(kSoftWarps * 32) : "memory");     // partials consumed; P, corr, l written
+        asm volatile("bar.sync 1, %0;" ::"n"(SW * 32) : "memory");     // partials consumed; P, corr, l written
         if (t == 0) {
           mbar_arrive(sempty_bar(buf));
           mbar_arrive(pfull_bar(buf));
@@ -451,22 +469,32 @@ bool decode_cross_absorbed_supported(int width, int heads, int head_dim, int n_k
          n_kv >= 1;
 }
 
-template <int T>
-static int launch_xa(const bf16* qp, const bf16* xn, bf16* ctx, int n, int heads, int n_kv, const unsigned char* finished,
+template <int T, int SW>
+static int launch_xa_sw(const bf16* qp, const bf16* xn, bf16* ctx, int n, int heads, int n_kv, const unsigned char* finished,
                      const DecodeState* st, int reverse, cudaStream_t stream) {
   using C = xa::Cfg<T>;
   static bool attr_done[64] = {};
   const int dev = current_device();
   EC_REQUIRE(dev >= 0 && dev < 64, EC_ERR_DEVICE, "no current CUDA device");
   if (!attr_done[dev]) {
-    EC_CHECK_CUDA(cudaFuncSetAttribute(xa::cross_absorbed_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    EC_CHECK_CUDA(cudaFuncSetAttribute(xa::cross_absorbed_kernel<T, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
     attr_done[dev] = true;
   }
   const int grid = std::min(n, num_sms());
   note_launches(1);
-  EC_CHECK_CUDA(launch_small_kernel(xa::cross_absorbed_kernel<T>, dim3(grid), dim3(xa::kThreads), (size_t)C::kSmem, stream, qp, xn,
-                              ctx, n, heads, n_kv, finished, st, reverse));
+  EC_CHECK_CUDA(launch_small_kernel(xa::cross_absorbed_kernel<T, SW>, dim3(grid), dim3(xa::kThreadsOf<SW>), (size_t)C::kSmem, stream,
+                                    qp, xn, ctx, n, heads, n_kv, finished, st, reverse));
   return EC_OK;
+}
+
+template <int T>
+static int launch_xa(const bf16* qp, const bf16* xn, bf16* ctx, int n, int heads, int n_kv, const unsigned char* finished,
+                     const DecodeState* st, int reverse, cudaStream_t stream) {
+  static const int env_sw = [] { const char* e = getenv("EC_XA_SOFT_WARPS"); return e ? atoi(e) : 3; }();
+  static const int env_ev = [] { const char* e = getenv("EC_XA_EVICT_FIRST"); return e ? atoi(e) : 1; }();
+  reverse = (reverse & 1) | (env_ev ? 2 : 0);
+  if (heads <= 12 && env_sw == 3) return launch_xa_sw<T, 3>(qp, xn, ctx, n, heads, n_kv, finished, st, reverse, stream);
+  return launch_xa_sw<T, 4>(qp, xn, ctx, n, heads, n_kv, finished, st, reverse, stream);
 }
 
 int decode_cross_absorbed(const bf16* qp, const bf16* xn, bf16* ctx, int batch, int heads, int width, int n_kv,

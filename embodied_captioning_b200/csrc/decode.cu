@@ -6,6 +6,10 @@
 #include "kernels.cuh"
 #include <cstdlib>
 
+#ifndef EC_SA_STREAM
+#define EC_SA_STREAM 1
+#endif
+
 namespace ec {
 
 // ---------------------------------------------------------------------------------------------------
@@ -212,12 +216,19 @@ __global__ void __launch_bounds__(kSaThreads, kSaMinBlocks) decode_self_attn_g8_
   const bf16* row = qkv + (size_t)b * 3 * C + h * D + sub * 8;
   bf16* kc = kcache + ((size_t)b * max_len) * C + h * D + sub * 8;
   bf16* vc = vcache + ((size_t)b * max_len) * C + h * D + sub * 8;
+  // K / V cache rows are a stream (2.3 GB over the 24 layers at 1024 crops, each row read once per step): ld.global.cs /
+  // st.global.cs mark them evict-first so that they do not flush the step's small hot set out of L2 (EC_SA_STREAM=0: plain)
   auto load_rows = [&](uint4 (&kk)[kSaR], uint4 (&vv)[kSaR], int j0, int limit) {
 #pragma unroll
     for (int r = 0; r < kSaR; ++r) {
       if (j0 + r < limit) {
+#if EC_SA_STREAM
+        kk[r] = __ldcs(reinterpret_cast<const uint4*>(kc + (size_t)(j0 + r) * C));
+        vv[r] = __ldcs(reinterpret_cast<const uint4*>(vc + (size_t)(j0 + r) * C));
+#else
         kk[r] = *reinterpret_cast<const uint4*>(kc + (size_t)(j0 + r) * C);
         vv[r] = *reinterpret_cast<const uint4*>(vc + (size_t)(j0 + r) * C);
+#endif
       }
     }
   };
@@ -235,8 +246,13 @@ __global__ void __launch_bounds__(kSaThreads, kSaMinBlocks) decode_self_attn_g8_
   const int pos = cur_len - 1;
   if (EC_SA_PREFETCH) load_rows(kn, vn, kSaR, pos);          // second batch, now that the length is known
   if (live) {
+#if EC_SA_STREAM
+    __stcs(reinterpret_cast<uint4*>(kc + (size_t)pos * C), knew);
+    __stcs(reinterpret_cast<uint4*>(vc + (size_t)pos * C), vnew);
+#else
     *reinterpret_cast<uint4*>(kc + (size_t)pos * C) = knew;
     *reinterpret_cast<uint4*>(vc + (size_t)pos * C) = vnew;
+#endif
   }
   auto dot8 = [&](const uint4& u) {
     const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);

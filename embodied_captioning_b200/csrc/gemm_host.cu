@@ -103,6 +103,10 @@ static int launch_tile(const GemmArgs& a, cudaStream_t stream) {
   const int S = (EPI == EPI_F32_RESID && a.split_k > 1) ? a.split_k : 1;
   p.split_k = S; p.sk_ws = a.sk_ws; p.sk_cnt = a.sk_cnt;
   const int tiles_m = ceil_div(a.M, kBM), tiles_n = ceil_div(a.N, BN);
+  // measured (profiles/r02_l2_policies.txt): +0.4 ms per decode -- the eight row-block CTAs that share a W tile do not
+  // arrive close enough together -- so the hint is opt-in (EC_W_EVICT_FIRST=1)
+  static const int env_wef = [] { const char* e = getenv("EC_W_EVICT_FIRST"); return e ? atoi(e) : 0; }();
+  p.w_evict_first = (env_wef != 0 && tiles_m <= 16) ? 1 : 0;
   EC_REQUIRE(S == 1 || tiles_m * tiles_n * S <= num_sms(), EC_ERR_UNSUPPORTED, "split-K needs one tile slice per SM");
   const int grid = std::min(tiles_m * tiles_n * S, num_sms());
   static bool attr_done[64] = {};   // per template instantiation and device
@@ -135,6 +139,7 @@ static int launch_pair_ew(const GemmArgs& a, cudaStream_t stream) {
   p.ln_g = a.ln_gamma; p.ln_b = a.ln_beta; p.ln_out = a.ln_out; p.ld_ln = a.ld_ln; p.ln_cnt = a.ln_counters;
   p.ln_tiles_n = ceil_div(a.N, BN);
   p.pf_ptr = nullptr; p.pf_bytes = 0; p.grp_cols = 0; p.split_k = 1; p.sk_ws = nullptr; p.sk_cnt = nullptr;
+  p.w_evict_first = 0;
   const int tiles_m = ceil_div(a.M, 2 * kBM), tiles_n = ceil_div(a.N, BN);
   const int clusters = std::min(tiles_m * tiles_n, num_sms() / 2);
   static bool attr_done[64] = {};   // per template instantiation and device
@@ -453,6 +458,7 @@ int gemm_reference_simt(const GemmArgs& a, GemmEpilogue epi, cudaStream_t stream
   p.n_parts = a.n_parts; p.eos_col = a.eos_col; p.cur_len = a.cur_len; p.min_len = a.min_len; p.skip_flag = nullptr;
   p.ln_g = nullptr; p.ln_b = nullptr; p.ln_out = nullptr; p.ld_ln = 0; p.ln_cnt = nullptr; p.ln_tiles_n = 0;
   p.pf_ptr = nullptr; p.pf_bytes = 0; p.grp_cols = a.group_cols; p.split_k = 1; p.sk_ws = nullptr; p.sk_cnt = nullptr;
+  p.w_evict_first = 0;
   dim3 grid(ceil_div(a.N, 128), a.M);
   gemm_simt_kernel<<<grid, 128, 0, stream>>>(a.A, a.lda, a.W, a.ldw, a.M, a.N, a.K, p, (int)epi);
   EC_POST_LAUNCH();

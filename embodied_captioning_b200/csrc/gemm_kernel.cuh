@@ -50,6 +50,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap,
       ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+// the same load with an L2 eviction policy (createpolicy)
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t smem_dst, const void* tmap, int c0, int c1, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
@@ -251,6 +268,11 @@ struct EpiParams {
   // slices run by adjacent CTAs.  Slices 1.. store their raw fp32 accumulators in sk_ws[slice - 1][M][N] and count
   // themselves on sk_cnt[tile]; slice 0 waits for them and adds them IN SLICE ORDER in its residual epilogue.
   int split_k; float* sk_ws; int* sk_cnt;
+  // 1-CTA kernel, opt-in: W tiles loaded with the L2 evict-first policy (the 557 MB of decoder weights are a stream
+  // that flushes the step's small hot set -- kernel parameters, tensor maps, biases, activations, code -- out of the
+  // 126 MB L2).  The same hint on the image-token and K / V-cache streams pays (cross_absorbed.cu, decode.cu); on the
+  // weights it measured +0.4 ms per decode.
+  int w_evict_first;
 };
 
 __device__ __forceinline__ float4 ld_cg_f4(const float* p);
@@ -602,11 +624,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     __syncwarp();
     const int m_blk = ((int)blockIdx.x / S) / tiles_n, n_blk = ((int)blockIdx.x / S) % tiles_n;
     const int a_k0 = (p.grp_cols > 0) ? (n_blk * BN / p.grp_cols) * K : 0;     // grouped GEMM: this tile's column slab of A
+    const uint64_t w_policy = p.w_evict_first ? ptx::policy_evict_first() : ptx::policy_evict_normal();
     for (int g = 0; g < pre; ++g) {               // warp-uniform loop, elected lane issues (see the MMA warp)
       if (ptx::elect_one()) {
         ptx::mbar_expect_tx(full_bar(g), Cfg::kStageBytes);
         ptx::tma_load_2d(smem_a0 + g * Cfg::kABytes, &tmap_a, a_k0 + (kb0 + g) * kBK, m_blk * kBM, full_bar(g));
-        ptx::tma_load_2d(smem_b0 + g * Cfg::kBBytes, &tmap_w, (kb0 + g) * kBK, n_blk * BN, full_bar(g));
+        ptx::tma_load_2d_hint(smem_b0 + g * Cfg::kBBytes, &tmap_w, (kb0 + g) * kBK, n_blk * BN, full_bar(g), w_policy);
       }
       __syncwarp();
     }
@@ -664,6 +687,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // k-blocks find the ring empty and skip the wait.
     {
       const int w = (warp == 0) ? 0 : 1;
+      const uint64_t w_policy = p.w_evict_first ? ptx::policy_evict_first() : ptx::policy_evict_normal();
       int g = 0;                                  // running k-block index of this CTA over all its tiles
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = (tile / S) / tiles_n, n_blk = (tile / S) % tiles_n;
@@ -678,7 +702,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (ptx::elect_one()) {
             ptx::mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
             ptx::tma_load_2d(smem_a0 + stage * Cfg::kABytes, &tmap_a, a_k0 + (kb0 + kb) * kBK, m_blk * kBM, full_bar(stage));
-            ptx::tma_load_2d(smem_b0 + stage * Cfg::kBBytes, &tmap_w, (kb0 + kb) * kBK, n_blk * BN, full_bar(stage));
+            ptx::tma_load_2d_hint(smem_b0 + stage * Cfg::kBBytes, &tmap_w, (kb0 + kb) * kBK, n_blk * BN, full_bar(stage), w_policy);
           }
           __syncwarp();
         }
