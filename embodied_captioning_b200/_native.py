@@ -29,8 +29,9 @@ EXPORTS = [
     "ec_textenc_create", "ec_textenc_destroy", "ec_textenc_set_tensor", "ec_textenc_finalize",
     "ec_textenc_workspace_bytes", "ec_textenc_encode",
     "ec_gemm_bf16_grouped", "ec_gemm_bf16_splitk", "ec_cross_attention_absorbed", "ec_pack_image_tokens", "ec_packed_image_tokens_bytes",
-    "ec_seq_timing_read",
+    "ec_seq_timing_read", "ec_gemm_timing_read",
 ]
+DEBUG_EXPORTS = ("ec_seq_timing_read", "ec_gemm_timing_read")      # absent from A/B builds of older sources
 
 
 class NativeError(RuntimeError):
@@ -115,9 +116,14 @@ def lib() -> C.CDLL:
     L.ec_launch_count.argtypes = []
     L.ec_launch_count.restype = C.c_int64
     L.ec_profile_gemm.argtypes = [i32]
-    L.ec_seq_timing_read.argtypes = [C.POINTER(C.c_int64), i32]
     L.ec_profile_gemm_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    ab_build = bool(os.environ.get("EC_LIB_PATH"))
+    for name in DEBUG_EXPORTS:
+        if hasattr(L, name):
+            getattr(L, name).argtypes = [C.POINTER(C.c_int64), i32]
     for name in EXPORTS:
+        if ab_build and name in DEBUG_EXPORTS:
+            continue
         getattr(L, name)          # AttributeError here means the .so is older than the header: rebuild
     _lib = L
     return L

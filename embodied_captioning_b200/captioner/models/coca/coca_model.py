@@ -67,7 +67,7 @@ class CoCa(nn.Module):
         self._tc_attention = True
         self._chains = 0
         self._absorbed = os.environ.get("EC_ABSORB", "1") != "0"     # A/B switch for probes
-        self._seq = None                                             # None: the library default (EC_SEQ, on)
+        self._seq = None                                             # None: the library default (EC_SEQ, off)
         self._dummy = nn.Parameter(torch.zeros(1), requires_grad=False)   # lets `.parameters()` work
 
     # ------------------------------------------------------------------ nn.Module protocol

@@ -327,6 +327,10 @@ int ec_profile_gemm_read(double* ms, double* flops, int64_t* launches) {
   return EC_OK;
 }
 
+int ec_gemm_timing_read(int64_t* out_host, int32_t count) {
+  return gemm_timing_read(reinterpret_cast<long long*>(out_host), count);
+}
+
 int ec_seq_timing_read(int64_t* out_host, int32_t count) {
   return gemm_seq_timing_read(reinterpret_cast<long long*>(out_host), count);
 }

@@ -357,6 +357,13 @@ bool gemm_seq_supported(const GemmSeqStage* st, int n) {
   return true;
 }
 
+int gemm_timing_read(long long* host, int count) {
+  EC_REQUIRE(host != nullptr && count > 0 && count <= kGemmTimingSlots * 12, EC_ERR_INVALID, "gemm_timing_read: bad arguments");
+  EC_CHECK_CUDA(cudaDeviceSynchronize());
+  EC_CHECK_CUDA(cudaMemcpyFromSymbol(host, g_gemm_timing, (size_t)count * sizeof(long long)));
+  return EC_OK;
+}
+
 int gemm_seq_timing_read(long long* host, int count) {
   const size_t total = (size_t)kSeqTimingTags * kSeqMaxStages * kSeqTimingEvents;
   EC_REQUIRE(host != nullptr && count > 0 && (size_t)count <= total, EC_ERR_INVALID, "gemm_seq_timing_read: bad arguments");

@@ -216,6 +216,18 @@ template <int BN> struct TileCfg {
 
 __device__ int g_gemm_watchdog = 0;
 
+// Stage clocks of CTA 0 of the 1-CTA kernel (-DEC_GEMM_TIMING builds; scripts/gemm_timing_probe.py): a ring of records
+// {N, K, BN * 8 + EPI, -, cycles since kernel entry at: skip word loaded, prologue done, first operands landed, last
+// MMA committed, accumulator ready, tile stored}.
+constexpr int kGemmTimingSlots = 8192;
+__device__ long long g_gemm_timing[kGemmTimingSlots][12];
+__device__ unsigned int g_gemm_timing_next = 0;
+#ifdef EC_GEMM_TIMING
+#define GEMM_T(ev) do { if (blockIdx.x == 0 && lane == 0) g_gemm_timing[t_slot][4 + (ev)] = clock64() - t_entry; } while (0)
+#else
+#define GEMM_T(ev) do { } while (0)
+#endif
+
 __device__ __forceinline__ bool bounded_wait(uint32_t bar, uint32_t parity, int code) {
   if (ptx::mbar_try_wait(bar, parity)) return true;
   long long t0 = clock64();
@@ -568,11 +580,90 @@ __device__ __forceinline__ void l2_prefetch_slice(const unsigned char* ptr, unsi
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Hand-over of rows between CTAs through counters in global memory (GEMM sequences, gemm_seq.cuh)
+__device__ __forceinline__ int seq_ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// release: everything this thread wrote -- and, through the named barrier before it, everything the CTA's epilogue
+// warps wrote -- is visible at GPU scope before the count
+__device__ __forceinline__ void seq_red_release(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// all lanes poll the same word (one broadcast L2 request per iteration); ONE warp per CTA polls a given counter
+__device__ __forceinline__ bool seq_wait_counter(const int* cnt, int target) {
+  if (seq_ld_acquire(cnt) >= target) return true;
+  const long long t0 = clock64();
+  while (seq_ld_acquire(cnt) < target) {
+    if (clock64() - t0 > kWatchdogCycles) { atomicExch(&g_gemm_watchdog, 6); return false; }
+  }
+  return true;
+}
+
+// LayerNorm of ONE row by one warp (same arithmetic as layernorm.cu): the row (L2: written microseconds ago by the
+// block's tiles) and gamma / beta (L2: prefetched at kernel entry) are requested together.
+__device__ __forceinline__ void ln_row_warp(const float* xr, int width, const float* ln_g, const float* ln_b, bf16* yr,
+                                            int lane) {
+  const int nvec = width >> 2;
+  float4 v[kLnTailMaxVec];
+#pragma unroll
+  for (int i = 0; i < kLnTailMaxVec; ++i) {
+    const int c = lane + i * 32;
+    v[i] = (c < nvec) ? ld_cg_f4(xr + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // gamma / beta: one 128-byte line per lane into L1 while the row is in flight (no registers held)
+  if (lane * 32 < width) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(ln_g + lane * 32));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(ln_b + lane * 32));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnTailMaxVec; ++i)
+    if (lane + i * 32 < nvec) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / (float)width;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnTailMaxVec; ++i) {
+    if (lane + i * 32 < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)width + 1e-5f);      // same arithmetic as layernorm.cu
+#pragma unroll
+  for (int i = 0; i < kLnTailMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(ln_g) + c), b = __ldg(reinterpret_cast<const float4*>(ln_b) + c);
+      uint2 pk;
+      pk.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+      pk.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+      reinterpret_cast<uint2*>(yr)[c] = pk;
+    }
+  }
+}
+__device__ __forceinline__ void seq_ln_row(const EpiParams& p, int row, int lane) {
+  ln_row_warp(reinterpret_cast<const float*>(p.out) + (size_t)row * p.ldo, p.N, p.ln_g, p.ln_b, p.ln_out + (size_t)row * p.ld_ln, lane);
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads1, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     EpiParams p, int K, int tiles_m, int tiles_n) {
   using Cfg = TileCfg<BN>;
+#ifdef EC_GEMM_TIMING
+  const long long t_entry = clock64();
+  __shared__ unsigned int s_t_slot;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    s_t_slot = atomicAdd(&g_gemm_timing_next, 1u) % kGemmTimingSlots;
+    g_gemm_timing[s_t_slot][0] = p.N; g_gemm_timing[s_t_slot][1] = K; g_gemm_timing[s_t_slot][2] = BN * 8 + EPI;
+    g_gemm_timing[s_t_slot][3] = p.M; g_gemm_timing[s_t_slot][10] = 0; g_gemm_timing[s_t_slot][11] = 0;
+  }
+#endif
   pdl_trigger_top();
   // The dependency wait comes first: without programmatic dependent launch (the default -- it measured slower inside
   // the step graphs) it is a no-op, and the skip flag's L2 round trip then overlaps the prologue instead of
@@ -586,6 +677,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t smem_b0 = smem_base + Cfg::kStages * Cfg::kABytes;
   const uint32_t smem_epi = smem_base + Cfg::kStages * Cfg::kStageBytes;
   const uint32_t bar0 = smem_epi + kEpiWarps * kEpiStageBytes;
+#ifdef EC_GEMM_TIMING
+  long long t_skip = 0;
+  if (skip_word >= 0) t_skip = clock64() - t_entry;      // after the skip word's round trip
+#endif
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * Cfg::kStages + s); };
@@ -606,7 +701,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // ---- prologue.  Warp 0 initialises the barriers and at once issues the loads of the first ring-full of
   // k-blocks: they need the barriers but neither the TMEM allocation nor the CTA-wide sync, and in a 6 us kernel
   // those ~0.3 us are worth having.
-  const int pre = (skip_word == 0 && (int)blockIdx.x < num_tiles) ? (num_kb < Cfg::kStages ? num_kb : Cfg::kStages) : 0;
+  // They do NOT wait for the skip word either (measured with -DEC_GEMM_TIMING: its round trip ends 0.6 us after kernel
+  // entry -- the first parameter fetch of a launch is cold -- and the first operands only landed at 1.6-2.0 us): a
+  // skipped launch drains them before it leaves.
+  const int pre = ((int)blockIdx.x < num_tiles) ? (num_kb < Cfg::kStages ? num_kb : Cfg::kStages) : 0;
   if (warp == 0) {
     if (lane == 0) {
       ptx::prefetch_tmap(&tmap_a);
@@ -642,6 +740,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+#ifdef EC_GEMM_TIMING
+  const unsigned int t_slot = s_t_slot;
+  if (warp == 0 && blockIdx.x == 0 && lane == 0) g_gemm_timing[t_slot][4] = t_skip;
+  if (warp == 0) GEMM_T(1);
+#endif
 
   const bool skip = skip_word != 0;
   // Dual-issuer mode (one tile per CTA, i.e. the small-M GEMMs of the decoder steps).  Measured: the K loop of a
@@ -652,7 +755,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const bool dual = (num_tiles <= (int)gridDim.x) && (num_kb >= 2) && kDualIssue;
 
   if (skip) {
-    // fall through to the teardown
+    // the prologue's loads must have landed before the CTA may exit
+    if (warp == 0)
+      for (int g = 0; g < pre; ++g) bounded_wait(full_bar(g), 0u, 1);
   } else if (warp == 2) {
     if (p.pf_ptr != nullptr) l2_prefetch_slice(p.pf_ptr, p.pf_bytes, lane);
   } else if (warp == 3 || (warp == 1 && dual)) {
@@ -666,6 +771,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint32_t phase = (uint32_t)((kb / Cfg::kStages) & 1);
         if (!bounded_wait(full_bar(stage), phase, 3)) goto done;
         ptx::tc_fence_after();
+        if (kb == 0) GEMM_T(2);
         const uint64_t adesc = adesc0 + (uint64_t)((stage * Cfg::kABytes) >> 4);
         const uint64_t bdesc = bdesc0 + (uint64_t)((stage * Cfg::kBBytes) >> 4);
         if (ptx::elect_one()) {
@@ -678,6 +784,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       if (ptx::elect_one()) ptx::umma_commit(tfull_bar(w));
       __syncwarp();
+      if (w == 0) GEMM_T(3);
     }
   } else if (warp == 0 || warp == kSecondProducerWarp) {
     // ===================================================================== TMA producers (warp-uniform loops, one
@@ -769,6 +876,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (!bounded_wait(tfull_bar(acc), acc_phase, 4)) break;
       if (dual && !bounded_wait(tfull_bar(1), 0u, 4)) break;      // second issuer's accumulator (stage 1)
       ptx::tc_fence_after();
+      if (e == 0) GEMM_T(4);
       if (S > 1 && slice == 0) {
         // the other slices of this tile (adjacent, co-resident CTAs) have stored their partial accumulators
         volatile int* cnt = p.sk_cnt + tile / S;
@@ -794,6 +902,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
       }
+      if (e == 0) GEMM_T(5);
       // release the accumulator stage back to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();

@@ -67,28 +67,6 @@ __device__ long long g_seq_timing[kSeqTimingTags][kSeqMaxStages][kSeqTimingEvent
 
 struct SeqMaps { CUtensorMap a[kSeqMaxStages]; CUtensorMap w[kSeqMaxStages]; };
 
-__device__ __forceinline__ int seq_ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// release: everything this thread wrote -- and, through the named barrier before it, everything the CTA's epilogue
-// warps wrote -- is visible at GPU scope before the count
-__device__ __forceinline__ void seq_red_release(int* p, int v) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// all lanes poll the same word (one broadcast L2 request per iteration); ONE warp per CTA polls a given counter
-__device__ __forceinline__ bool seq_wait_counter(const int* cnt, int target) {
-  if (seq_ld_acquire(cnt) >= target) return true;
-  const long long t0 = clock64();
-  while (seq_ld_acquire(cnt) < target) {
-    if (clock64() - t0 > kWatchdogCycles) { atomicExch(&g_gemm_watchdog, 6); return false; }
-  }
-  return true;
-}
-
 __device__ __forceinline__ uint32_t seq_idesc(int bn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 }
@@ -101,50 +79,6 @@ __device__ __forceinline__ void seq_epilogue_bn(const EpiParams& p, int bn, uint
   else if constexpr (EPI != EPI_F32_RESID) {
     if (bn == 192) epilogue_tile<192, EPI>(p, tmem_acc, row0, n_blk, quad, half, lane, stg, 0, acc2_off, 0);
     else epilogue_tile<256, EPI>(p, tmem_acc, row0, n_blk, quad, half, lane, stg, 0, acc2_off, 0);
-  }
-}
-
-// LayerNorm of ONE row by one warp (same arithmetic as layernorm.cu): the row (L2: written microseconds ago by the
-// block's tiles) and gamma / beta (L2: prefetched at kernel entry) are requested together.
-__device__ __forceinline__ void seq_ln_row(const EpiParams& p, int row, int lane) {
-  const int width = p.N, nvec = width >> 2;
-  const float* xr = reinterpret_cast<const float*>(p.out) + (size_t)row * p.ldo;
-  float4 v[kLnTailMaxVec];
-#pragma unroll
-  for (int i = 0; i < kLnTailMaxVec; ++i) {
-    const int c = lane + i * 32;
-    v[i] = (c < nvec) ? ld_cg_f4(xr + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  // gamma / beta: one 128-byte line per lane into L1 while the row is in flight (no registers held)
-  if (lane * 32 < width) {
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p.ln_g + lane * 32));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p.ln_b + lane * 32));
-  }
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < kLnTailMaxVec; ++i)
-    if (lane + i * 32 < nvec) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  const float mean = warp_sum(s) / (float)width;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < kLnTailMaxVec; ++i) {
-    if (lane + i * 32 < nvec) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      q += (a * a + b * b) + (c * c + d * d);
-    }
-  }
-  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)width + 1e-5f);      // same arithmetic as layernorm.cu
-  bf16* yr = p.ln_out + (size_t)row * p.ld_ln;
-#pragma unroll
-  for (int i = 0; i < kLnTailMaxVec; ++i) {
-    const int c = lane + i * 32;
-    if (c < nvec) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_g) + c), b = __ldg(reinterpret_cast<const float4*>(p.ln_b) + c);
-      uint2 pk;
-      pk.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
-      pk.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
-      reinterpret_cast<uint2*>(yr)[c] = pk;
-    }
   }
 }
 

@@ -77,6 +77,8 @@ int gemm_seq(const GemmSeqStage* st, int n, int* counters, const int* skip_flag,
              size_t prefetch_bytes, cudaStream_t stream, int timing_tag = -1);
 // stage clocks of CTA 0 recorded by -DEC_SEQ_TIMING builds: [64 tags][6 stages][16 events] cycles (zeros otherwise)
 int gemm_seq_timing_read(long long* host, int count);
+// -DEC_GEMM_TIMING builds: ring of 8192 records x 10 of CTA 0 of the 1-CTA kernel (gemm_kernel.cuh)
+int gemm_timing_read(long long* host, int count);
 
 // Test / debug helper: plain SIMT reference GEMM with the same epilogues (used by the unit tests to
 // cross-check the tensor-core kernel on device; never called by the model path).

@@ -538,6 +538,17 @@ size_t Model::decode_workspace_bytes(int n, int seq_len) const {
   return carve_decode(*this, nullptr, std::max(n, 1), std::max(seq_len, 2)).bytes;
 }
 
+// w.ln = LayerNorm(w.x; g, b), then out = epi(w.ln W^T + bias).  (Round 2 also tried the LayerNorm as a PRE-PHASE of the
+// consuming GEMM -- its epilogue warps normalise the rows during the launch's cold start and hand them to the TMA producers
+// through row-block counters: bit-identical, 92.4 vs 85.8 ms per decode, and 1.4 ms slower even when switched off;
+// removed, profiles/r02_gemm_timing.txt.)
+int Model::ln_linear(const DecodeWs& w, const float* g, const float* b, const bf16* W, const float* bias, int n, int N,
+                     void* out, int ldo, GemmEpilogue epi, const int* skip, Prefetch pf, cudaStream_t s) {
+  const int T = cfg.text_width;
+  EC_TRY(layernorm(w.x, T, g, b, w.ln, T, true, n, T, skip, s));
+  return linear(w.ln, T, W, T, bias, n, N, T, out, ldo, epi, nullptr, 0, skip, s, nullptr, pf);
+}
+
 // `ln1_done`: w.ln already holds ln_1(x) (written by the previous block's fused tail); `next_g/next_b`: the LayerNorm
 // that follows this block (next block's ln_1 or ln_final), fused into c_proj when `fuse_ln` is on.
 int Model::self_block(const Block& b, const DecodeWs& w, bf16* kc, bf16* vc, int n, int max_len, int heads,
@@ -545,19 +556,25 @@ int Model::self_block(const Block& b, const DecodeWs& w, bf16* kc, bf16* vc, int
   const int T = cfg.text_width;
   const int* skip = &w.st->done;
   const bool fuse = decoder_fuse(n);
-  if (!ln1_done) EC_TRY(layernorm(w.x, T, b.ln1_g, b.ln1_b, w.ln, T, true, n, T, skip, s));
   const size_t TT = (size_t)T * T * sizeof(bf16);
   const Prefetch none;
   // every GEMM pulls the next GEMM's weights into L2 (the 557 MB of decoder weights cycle through L2 once per step)
-  EC_TRY(linear(w.ln, T, b.w_qkv, T, b.b_qkv, n, 3 * T, T, w.qkv, 3 * T, EPI_BF16, nullptr, 0, skip, s, nullptr,
-                prefetch_weights ? Prefetch{b.w_out, TT} : none));
+  if (!ln1_done)
+    EC_TRY(ln_linear(w, b.ln1_g, b.ln1_b, b.w_qkv, b.b_qkv, n, 3 * T, w.qkv, 3 * T, EPI_BF16, skip,
+                     prefetch_weights ? Prefetch{b.w_out, TT} : none, s));
+  else
+    EC_TRY(linear(w.ln, T, b.w_qkv, T, b.b_qkv, n, 3 * T, T, w.qkv, 3 * T, EPI_BF16, nullptr, 0, skip, s, nullptr,
+                  prefetch_weights ? Prefetch{b.w_out, TT} : none));
   EC_TRY(decode_self_attention(w.qkv, kc, vc, w.att, n, heads, T / heads, max_len, w.finished, w.st, s));
   FusedLn ln2{b.ln2_g, b.ln2_b, fuse ? w.ln : nullptr, T, w.ln_cnt};
   EC_TRY(linear(w.att, T, b.w_out, T, b.b_out, n, T, T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &ln2,
                 prefetch_weights ? Prefetch{b.w_fc1, 4 * TT} : none));
-  if (!fuse) EC_TRY(layernorm(w.x, T, b.ln2_g, b.ln2_b, w.ln, T, true, n, T, skip, s));
-  EC_TRY(linear(w.ln, T, b.w_fc1, T, b.b_fc1, n, 4 * T, T, w.fc1, 4 * T, EPI_BF16_GELU, nullptr, 0, skip, s, nullptr,
-                prefetch_weights ? Prefetch{b.w_fc2, 4 * TT} : none));
+  if (!fuse)
+    EC_TRY(ln_linear(w, b.ln2_g, b.ln2_b, b.w_fc1, b.b_fc1, n, 4 * T, w.fc1, 4 * T, EPI_BF16_GELU, skip,
+                     prefetch_weights ? Prefetch{b.w_fc2, 4 * TT} : none, s));
+  else
+    EC_TRY(linear(w.ln, T, b.w_fc1, T, b.b_fc1, n, 4 * T, T, w.fc1, 4 * T, EPI_BF16_GELU, nullptr, 0, skip, s, nullptr,
+                  prefetch_weights ? Prefetch{b.w_fc2, 4 * TT} : none));
   FusedLn nxt{next_g, next_b, fuse ? w.ln : nullptr, T, w.ln_cnt};
   EC_TRY(linear(w.fc1, 4 * T, b.w_fc2, 4 * T, b.b_fc2, n, T, 4 * T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &nxt,
                 prefetch_weights ? next_pf : none, SplitK{w.sk_ws, w.sk_cnt}));
@@ -570,11 +587,14 @@ int Model::cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int la
   const int T = cfg.text_width, NK = cfg.n_queries - 1;
   const int* skip = &w.st->done;
   const bool fuse = decoder_fuse(n);
-  if (!ln1_done) EC_TRY(layernorm(w.x, T, b.ln1_g, b.ln1_b, w.ln, T, true, n, T, skip, s));
   const size_t TT = (size_t)T * T * sizeof(bf16);
   const Prefetch none;
-  EC_TRY(linear(w.ln, T, b.w_qkv, T, b.b_qkv, n, T, T, w.q, T, EPI_BF16, nullptr, 0, skip, s, nullptr,
-                prefetch_weights ? Prefetch{b.w_out, TT} : none));   // q rows only
+  if (!ln1_done)
+    EC_TRY(ln_linear(w, b.ln1_g, b.ln1_b, b.w_qkv, b.b_qkv, n, T, w.q, T, EPI_BF16, skip,
+                     prefetch_weights ? Prefetch{b.w_out, TT} : none, s));   // q rows only
+  else
+    EC_TRY(linear(w.ln, T, b.w_qkv, T, b.b_qkv, n, T, T, w.q, T, EPI_BF16, nullptr, 0, skip, s, nullptr,
+                  prefetch_weights ? Prefetch{b.w_out, TT} : none));   // q rows only
   if (layer >= 0) {
     // absorbed form (cross_absorbed.cu): q' = per-head W_k^T q / 8 (grouped GEMM, K = 64), one pass over the normalised
     // image tokens, then the per-head V projection of the contexts (grouped GEMM, K = T) -> w.att
@@ -595,9 +615,12 @@ int Model::cross_block(const Block& b, const DecodeWs& w, const bf16* kv, int la
   FusedLn ln2{b.ln2_g, b.ln2_b, fuse ? w.ln : nullptr, T, w.ln_cnt};
   EC_TRY(linear(w.att, T, b.w_out, T, b.b_out, n, T, T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &ln2,
                 prefetch_weights ? Prefetch{b.w_fc1, 4 * TT} : none));
-  if (!fuse) EC_TRY(layernorm(w.x, T, b.ln2_g, b.ln2_b, w.ln, T, true, n, T, skip, s));
-  EC_TRY(linear(w.ln, T, b.w_fc1, T, b.b_fc1, n, 4 * T, T, w.fc1, 4 * T, EPI_BF16_GELU, nullptr, 0, skip, s, nullptr,
-                prefetch_weights ? Prefetch{b.w_fc2, 4 * TT} : none));
+  if (!fuse)
+    EC_TRY(ln_linear(w, b.ln2_g, b.ln2_b, b.w_fc1, b.b_fc1, n, 4 * T, w.fc1, 4 * T, EPI_BF16_GELU, skip,
+                     prefetch_weights ? Prefetch{b.w_fc2, 4 * TT} : none, s));
+  else
+    EC_TRY(linear(w.ln, T, b.w_fc1, T, b.b_fc1, n, 4 * T, T, w.fc1, 4 * T, EPI_BF16_GELU, nullptr, 0, skip, s, nullptr,
+                  prefetch_weights ? Prefetch{b.w_fc2, 4 * TT} : none));
   FusedLn nxt{next_g, next_b, fuse ? w.ln : nullptr, T, w.ln_cnt};
   EC_TRY(linear(w.fc1, 4 * T, b.w_fc2, 4 * T, b.b_fc2, n, T, 4 * T, w.x, T, EPI_F32_RESID, w.x, T, skip, s, &nxt,
                 prefetch_weights ? next_pf : none, SplitK{w.sk_ws, w.sk_cnt}));

@@ -114,6 +114,8 @@ struct Model {
                      float* logits, bool teacher_forced, cudaStream_t s);
   int run_stages(const GemmSeqStage* st, int ns, int* counters, const int* skip, Prefetch pf, int n, cudaStream_t s,
                  int tag = -1);
+  int ln_linear(const DecodeWs& w, const float* g, const float* b, const bf16* W, const float* bias, int n, int N, void* out,
+                int ldo, GemmEpilogue epi, const int* skip, Prefetch pf, cudaStream_t s);
   int vocab_head(const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len, float* logits,
                  bool teacher_forced, cudaStream_t s);
   int decode_step(const DecodeWs& w, int* tokens, int ld_tokens, int n, int n_total, int seq_len, int min_len,

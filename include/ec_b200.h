@@ -209,6 +209,8 @@ int ec_profile_gemm_read(double* ms, double* flops, int64_t* launches);   /* sum
 /* Stage clocks of the decoder's GEMM-sequence kernel (csrc/gemm_seq.cuh), recorded by CTA 0 in builds with
  * -DEC_SEQ_TIMING (zeros otherwise): [64 launches of a step][6 stages][16 events] SM cycles since kernel entry. */
 int ec_seq_timing_read(int64_t* out_host, int32_t count);
+/* The same for the stand-alone small-M GEMM kernel (-DEC_GEMM_TIMING): a ring of 8192 records x 10 (gemm_kernel.cuh). */
+int ec_gemm_timing_read(int64_t* out_host, int32_t count);
 
 #ifdef __cplusplus
 }
