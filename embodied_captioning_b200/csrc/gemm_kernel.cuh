@@ -210,7 +210,9 @@ template <int BN> struct TileCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (BN == 192) ? 512 : 2 * BN;   // two accumulator stages (allocations are powers of 2)
   static constexpr int kBarBytes = 1024;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + kBarBytes + 1024 /*align*/;
+  // BN = 192 (the decoder's FC1 + GELU): four more staging buffers for the warps that help with the epilogue
+  static constexpr int kHelpWarps = (BN == 192) ? 4 : 0;
+  static constexpr int kSmemBytes = kStages * kStageBytes + (kEpiWarps + kHelpWarps) * kEpiStageBytes + kBarBytes + 1024 /*align*/;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 
@@ -303,6 +305,8 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, uint32_t tadd
   // The residual may alias the output (in-place residual stream): every element is read and written by the same
   // thread.  All eight loads of the chunk are issued before the TMEM load and the transpose so that their latency
   // is hidden (prefetching a whole chunk further ahead measured no better: 822 vs 842 TFLOP/s on out_proj).
+  // (Requesting them even earlier -- while the K loop runs -- measured WORSE: the K loop is bound by the SM's L2 ingest
+  // and the extra 32 KB per CTA slowed it from 1.7 to 2.1 us, profiles/r02_gemm_timing.txt.)
   float4 rsd[8];
   if (EPI == EPI_F32_RESID) {
 #pragma unroll
@@ -445,6 +449,28 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
     const size_t slot = (size_t)(row0 + lane) * p.n_parts + (size_t)(n_blk * 2 + half);
     p.part_val[slot] = best_v;
     p.part_idx[slot] = best_i;
+  }
+}
+
+// The same for an explicit set of 32-column chunks of the tile (bit c of `mask` = columns [32 c, 32 c + 32)): the GELU
+// epilogue of a lone 128 x 192 tile shared by THREE warps per TMEM lane quadrant (see gemm_tcgen05_kernel).
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile_chunks(const EpiParams& p, uint32_t tmem_acc, int row0, int n_blk, int quad,
+                                                     uint32_t mask, int lane, uint32_t stg, uint32_t acc2_off) {
+  static_assert(EPI == EPI_BF16 || EPI == EPI_BF16_GELU, "chunk-wise epilogue: bf16 outputs only");
+  float best_v = 0.f; int best_i = 0;
+  const bool rows_full = row0 + 32 <= p.M;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    if (((mask >> c) & 1u) == 0u) continue;
+    const int col_in_tile = c * 32;
+    const int gcol0 = n_blk * BN + col_in_tile;
+    const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)col_in_tile;
+    if (gcol0 >= p.N) continue;
+    if (rows_full && gcol0 + 32 <= p.N)
+      epilogue_chunk<BN, EPI, true>(p, taddr, row0, gcol0, lane, stg, 0, best_v, best_i, acc2_off, 0);
+    else
+      epilogue_chunk<BN, EPI, false>(p, taddr, row0, gcol0, lane, stg, 0, best_v, best_i, acc2_off, 0);
   }
 }
 
@@ -887,8 +913,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         __threadfence();
       }
-      epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m_blk * kBM + quad * 32, n_blk, quad, half, lane, stg,
-                             cur_len, dual ? (uint32_t)BN : 0u, slice);
+      if constexpr (EPI == EPI_BF16_GELU && BN == 192) {
+        // a lone tile (decoder FC1): warps 0..3 take chunks 2 and 5 of their lane quadrant once their own roles are
+        // done (below), this warp the other two of its half -- 2 instead of 3 chunks on the critical path (the GELU
+        // epilogue of a 128 x 192 tile on 8 warps was 3.4 of the launch's 7.7 us, profiles/r02_gemm_timing.txt)
+        if (dual)
+          epilogue_tile_chunks<BN, EPI>(p, tmem_base, m_blk * kBM + quad * 32, n_blk, quad, half ? 0x18u : 0x03u, lane, stg,
+                                        (uint32_t)BN);
+        else
+          epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m_blk * kBM + quad * 32, n_blk, quad, half, lane, stg,
+                                 cur_len, 0u, slice);
+      } else {
+        epilogue_tile<BN, EPI>(p, tmem_base + (uint32_t)(acc * BN), m_blk * kBM + quad * 32, n_blk, quad, half, lane, stg,
+                               cur_len, dual ? (uint32_t)BN : 0u, slice);
+      }
       if (S > 1) {
         __syncwarp();
         if (lane == 0) {
@@ -912,6 +950,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         ln_tail(p, m_blk * kBM, e, kEpiWarps, lane, 1, reinterpret_cast<volatile int*>(tmem_slot_ptr + 1));
     }
     pdl_trigger_bottom();    // per-CTA trigger: the first epilogue warp that has stored its last tile
+  }
+  if constexpr (EPI == EPI_BF16_GELU && BN == 192) {
+    // epilogue helpers: warp w (producer, issuers, allocator -- their loops are over) owns TMEM lane quadrant w
+    if (!skip && dual && warp < 4 && (int)blockIdx.x < num_tiles) {
+      const int m_blk = (int)blockIdx.x / tiles_n, n_blk = (int)blockIdx.x % tiles_n;
+      if (!bounded_wait(tfull_bar(0), 0u, 4) || !bounded_wait(tfull_bar(1), 0u, 4)) goto done;
+      ptx::tc_fence_after();
+      epilogue_tile_chunks<BN, EPI>(p, tmem_base, m_blk * kBM + warp * 32, n_blk, warp, 0x24u, lane,
+                                    smem_epi + (uint32_t)(kEpiWarps + warp) * kEpiStageBytes, (uint32_t)BN);
+    }
   }
 done:
   ptx::tc_fence_before();
