@@ -24,19 +24,25 @@
 // -- made the copy issue the critical path, 127 us per launch at 1024 crops); the ring runs ahead across crop
 // boundaries.  (The kernel reads "32" wherever the chunk size kKC appears in this comment.)
 //
-// Warp-specialised, 21 warps, every role on its own chunk at any moment:
-//   * producer warp: one bulk copy per chunk (and per crop's Q');
-//   * SCORE group, 8 warps: warp w contracts its T/8 slice of the feature dimension for all 32 keys of a chunk (Q'
-//     fragments stay in registers for the whole crop) and stores a partial 16 x 32 tile (double-buffered);
-//   * SOFTMAX group, 4 warps: sums the 8 partial tiles, online softmax, publishes P (bf16), the rescale factors and the
-//     running normaliser in one of two buffers;
+// Warp-specialised, 20 warps (<= 12 heads; 21 for 16), every role on its own chunk at any moment:
+//   * producer warp: one bulk copy per chunk, carrying the L2 evict-first policy (the tokens are a 0.4 GB stream);
+//   * SCORE group, 8 warps: warp w contracts its T/8 slice of the feature dimension for all 32 keys of a chunk and
+//     stores a partial 16 x 32 tile.  Its Q' fragments stay in registers for the whole crop and come straight from
+//     global memory (the next crop's are requested while this crop streams): no shared memory is spent on Q';
+//   * SOFTMAX group, 3 warps (12 rows x 8 threads; 4 warps for 16 heads): sums the 8 partial tiles, online softmax,
+//     publishes P (bf16), the rescale factors and the running normaliser in one of two buffers;
 //   * CONTEXT group, 8 warps: warp w owns T/8 output columns, C = corr * C + P X^ with ldmatrix.trans fragments of the
 //     same stage.
-// mbarriers: full / empty per stage (released by the 16 MMA warps), sfull / sempty per partial buffer, pfull / pempty
-// per P buffer, qfull / qempty for Q'.  Measured on B200 at 1024 crops (profiles/r02_xattn.txt): all warps doing both
-// phases in lock-step with two __syncthreads per chunk ran 90 us per launch with 8 warps (latency-bound: issue slots
-// 16 % busy) and 96 us with 16 warps (shared-memory pipe 69 % busy: twice the partial-tile traffic); score + softmax in
-// one group next to a context group 92 us (the context group waited on the score group's serial S -> softmax chain).
+// mbarriers: full / empty per stage (released by the 16 MMA warps), sfull / sempty for the partial tiles, pfull / pempty
+// per P buffer.  Measured on B200 at 1024 crops (profiles/r02_xattn.txt, r02_gemm_seq.txt, r02_l2_policies.txt): all
+// warps doing both phases in lock-step with two __syncthreads per chunk ran 90 us per launch with 8 warps (latency-bound:
+// issue slots 16 % busy) and 96 us with 16 warps (shared-memory pipe 69 % busy: twice the partial-tile traffic); score +
+// softmax in one group next to a context group 92 us (the context group waited on the score group's serial S -> softmax
+// chain); the three groups with a 3-stage ring and 21 warps 84.5 us under ncu (80 registers per thread: the context
+// warps serialised LDSM.T -> 2 HMMA through one register quad, and a deeper ring changed nothing); 20 warps = 96
+// registers 82.8 us, and THEN the fourth ring stage (bought by taking Q' out of shared memory and single-buffering the
+// partial tiles) pays: 84.0 -> 79.9 us per launch in scripts/xattn_probe.py, decode 83.7 -> 82.0 ms.  Eight stages of
+// 16 keys: 90.1 us (twice the hand-overs).
 #include "kernels.cuh"
 
 namespace ec {
@@ -47,7 +53,14 @@ namespace xa {
 #define EC_XA_KC 32
 #endif
 constexpr int kKC = EC_XA_KC;    // keys per chunk (16 or 32)
-constexpr int kNS = 96 / kKC;    // ring depth (chunks): the ring holds 96 keys, all but one chunk of it in flight
+#ifndef EC_XA_RING_KEYS
+#define EC_XA_RING_KEYS 128
+#endif
+constexpr int kNS = EC_XA_RING_KEYS / kKC;   // ring depth (chunks): the ring holds 128 keys, all but one chunk of it in flight
+#ifndef EC_XA_SP_BUFS
+#define EC_XA_SP_BUFS 1
+#endif
+constexpr int kSB = EC_XA_SP_BUFS;           // partial-score buffers between the score and the softmax group (1 or 2)
 constexpr int kKPT = kKC / 8;    // keys per softmax thread
 constexpr int kPrefetch = 0;     // L2 prefetch ahead of the ring: measured WORSE (125 vs 92 us, 667 vs 426 MB of DRAM reads)
 constexpr int kGroupWarps = 8;   // warps of the score group; the context group has as many
@@ -61,15 +74,13 @@ constexpr int kPLd = kKC + 8;    // bf16 per row of the probability tile (confli
 template <int T> struct Cfg {
   static constexpr int kRowBytes = T * 2 + 16;
   static constexpr int kStageBytes = kKC * kRowBytes;
-  static constexpr int kQRowBytes = T * 2;             // Q' rows are staged unpadded (one contiguous copy per crop)
-  static constexpr int kQBytes = 16 * kQRowBytes;
   static constexpr int kSpBufBytes = kGroupWarps * 16 * kSpLd * 4;
-  static constexpr int kSpBytes = 2 * kSpBufBytes;     // double-buffered between the score and the softmax group
+  static constexpr int kSpBytes = kSB * kSpBufBytes;
   static constexpr int kPBytes = 2 * 16 * kPLd * 2;    // double-buffered between the softmax and the context group
   static constexpr int kStatBytes = 2 * 2 * 16 * 4;    // corr[2][16], l[2][16]
-  static constexpr int kBarBytes = 256;               // full/empty[kNS], sfull/sempty[2], pfull/pempty[2], qfull, qempty
-  static_assert((2 * kNS + 10) * 8 <= kBarBytes, "barrier block too small");
-  static constexpr int kSmem = kNS * kStageBytes + kQBytes + kSpBytes + kPBytes + kStatBytes + kBarBytes + 128;
+  static constexpr int kBarBytes = 256;               // full/empty[kNS], sfull/sempty[2], pfull/pempty[2]
+  static_assert((2 * kNS + 8) * 8 <= kBarBytes, "barrier block too small");
+  static constexpr int kSmem = kNS * kStageBytes + kSpBytes + kPBytes + kStatBytes + kBarBytes + 128;
   static_assert(kSmem <= 227 * 1024, "shared memory budget exceeded");
   static_assert(T % (kGroupWarps * 16) == 0, "feature width must split into 16-wide k-steps per warp");
   static_assert(kKC == 32 || kKC == 16, "the softmax maps 8 threads onto the keys of a chunk");
@@ -154,10 +165,9 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t stage0 = base;
-  const uint32_t qs = base + kNS * C::kStageBytes;
-  float* sp = reinterpret_cast<float*>(gen + kNS * C::kStageBytes + C::kQBytes);          // [2][8 warps][16][kSpLd]
+  float* sp = reinterpret_cast<float*>(gen + kNS * C::kStageBytes);                       // [kSB][8 warps][16][kSpLd]
   uint8_t* pb_gen = reinterpret_cast<uint8_t*>(sp) + C::kSpBytes;                          // P[2][16][kPLd] bf16
-  const uint32_t pb = qs + C::kQBytes + C::kSpBytes;
+  const uint32_t pb = base + kNS * C::kStageBytes + C::kSpBytes;
   float* stat = reinterpret_cast<float*>(pb_gen + C::kPBytes);                             // corr[2][16], l[2][16]
   const uint32_t bar0 = pb + C::kPBytes + C::kStatBytes;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -166,8 +176,6 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
   auto sempty_bar = [&](int b) { return bar0 + 8u * (2 * kNS + 2 + b); };
   auto pfull_bar = [&](int b) { return bar0 + 8u * (2 * kNS + 4 + b); };
   auto pempty_bar = [&](int b) { return bar0 + 8u * (2 * kNS + 6 + b); };
-  const uint32_t qfull_bar = bar0 + 8u * (2 * kNS + 8);
-  const uint32_t qempty_bar = bar0 + 8u * (2 * kNS + 9);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, q4 = lane & 3;
@@ -195,15 +203,8 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
       mbar_init(pfull_bar(b), 1);                     // the softmax group published P / corr / l
       mbar_init(pempty_bar(b), kGroupWarps);          // every context warp consumed them
     }
-    mbar_init(qfull_bar, 1);
-    mbar_init(qempty_bar, kGroupWarps);               // every score warp holds its Q' fragments in registers
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  {
-    uint4* z = reinterpret_cast<uint4*>(gen + kNS * C::kStageBytes);
-    for (int i = tid; i < C::kQBytes / 16; i += kThreadsOf<SW>) z[i] = make_uint4(0, 0, 0, 0);
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic zero-fill before the async-proxy copies
   __syncthreads();
 
   const int first = next_active((int)blockIdx.x);
@@ -230,14 +231,7 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
       if (++pf_chunk == nchunks) { pf_chunk = 0; pf_crop = next_active(pf_crop + (int)gridDim.x); }
     };
     if (kPrefetch > 0) for (int i = 0; i < kPrefetch; ++i) prefetch_next();
-    for (int it = 0, cb = first; cb < n; cb = next_active(cb + (int)gridDim.x), ++it) {
-      if (!mbar_wait(qempty_bar, (uint32_t)((it & 1) ^ 1))) return;        // score warps hold the previous Q' in registers
-      if (lane == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(qfull_bar, (uint32_t)heads * (uint32_t)C::kQRowBytes);
-        if (evict_first) bulk_g2s_hint(qs, qp + (size_t)crop_of(cb) * heads * T, (uint32_t)heads * (uint32_t)C::kQRowBytes, qfull_bar, policy);
-        else bulk_g2s(qs, qp + (size_t)crop_of(cb) * heads * T, (uint32_t)heads * (uint32_t)C::kQRowBytes, qfull_bar);
-      }
+    for (int cb = first; cb < n; cb = next_active(cb + (int)gridDim.x)) {
       for (int c = 0; c < nchunks; ++c, ++gi) {
         const int stage = gi % kNS;
         if (kPrefetch > 0) prefetch_next();
@@ -254,20 +248,35 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
     }
   } else if (warp < kGroupWarps) {
     // =============================================================== score group: partial S = Q' X^T per warp
-    int gu = 0;
-    for (int it = 0, cb = first; cb < n; cb = next_active(cb + (int)gridDim.x), ++it) {
-      // the crop's absorbed queries: A fragments of Q' (16 x T, this warp's DPW columns) stay in registers
-      if (!mbar_wait(qfull_bar, (uint32_t)(it & 1))) return;
-      uint32_t qa[KS][4];
+    // The crop's absorbed queries: the A fragments of Q' (16 x T, this warp's DPW columns) stay in registers for the
+    // whole crop.  They come straight from global memory (L2: the grouped GEMM before this kernel wrote them) in the
+    // m16n8k16 fragment layout -- lane (g, q4) holds rows g / g + 8, columns 2 q4 and 8 + 2 q4 of every 16-wide k-step
+    // -- and the NEXT crop's are requested while this crop's chunks stream, so no shared memory is spent on Q' (it
+    // buys a fourth ring stage) and the crop boundary costs no round trip.  Rows past `heads` are zero.
+    auto load_q = [&](uint32_t (&dst)[KS][4], int b) {
+      const uint32_t* r_lo = reinterpret_cast<const uint32_t*>(qp + ((size_t)crop_of(b) * heads + g) * T + warp * DPW) + q4;
+      const uint32_t* r_hi = r_lo + (size_t)8 * T / 2;
+      const bool lo = g < heads, hi = g + 8 < heads;
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks)
-        ldsm_x4(qa[ks], qs + (lane & 15) * C::kQRowBytes + (warp * DPW + ks * 16 + (lane >> 4) * 8) * 2);
-      __threadfence_block();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(qempty_bar);
+      for (int ks = 0; ks < KS; ++ks) {
+        dst[ks][0] = lo ? __ldg(r_lo + ks * 8) : 0u;
+        dst[ks][1] = hi ? __ldg(r_hi + ks * 8) : 0u;
+        dst[ks][2] = lo ? __ldg(r_lo + ks * 8 + 4) : 0u;
+        dst[ks][3] = hi ? __ldg(r_hi + ks * 8 + 4) : 0u;
+      }
+    };
+    int gu = 0;
+    uint32_t qa[KS][4], qn[KS][4];
+    load_q(qn, first);
+    for (int cb = first; cb < n;) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) { qa[ks][0] = qn[ks][0]; qa[ks][1] = qn[ks][1]; qa[ks][2] = qn[ks][2]; qa[ks][3] = qn[ks][3]; }
+      const int cb_next = next_active(cb + (int)gridDim.x);
+      if (cb_next < n) load_q(qn, cb_next);
+      cb = cb_next;
 
       for (int c = 0; c < nchunks; ++c, ++gu) {
-        const int stage = gu % kNS, sb = gu & 1;
+        const int stage = gu % kNS, sb = gu % kSB;
         const uint32_t sbase = stage0 + stage * C::kStageBytes;
         if (!mbar_wait(full_bar(stage), (uint32_t)((gu / kNS) & 1))) return;
         float s[kKC / 8][4];
@@ -284,7 +293,7 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
             mma16816(s[2 * np + 1], qa[ks], b[2], b[3]);
           }
         }
-        if (!mbar_wait(sempty_bar(sb), (uint32_t)(((gu >> 1) & 1) ^ 1))) return;    // softmax consumed chunk gu - 2
+        if (!mbar_wait(sempty_bar(sb), (uint32_t)(((gu / kSB) & 1) ^ 1))) return;    // softmax consumed chunk gu - kSB
         {
           float* my = sp + (sb * kGroupWarps + warp) * 16 * kSpLd;
 #pragma unroll
@@ -357,12 +366,12 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
     for (int cb = first; cb < n; cb = next_active(cb + (int)gridDim.x)) {
       float m_run = -INFINITY, l_run = 0.f;      // softmax state of row r (replicated over its 8 threads)
       for (int c = 0; c < nchunks; ++c, ++gu) {
-        const int buf = gu & 1;
-        if (!mbar_wait(sfull_bar(buf), (uint32_t)((gu >> 1) & 1))) return;
+        const int buf = gu & 1, sb = gu % kSB;
+        if (!mbar_wait(sfull_bar(sb), (uint32_t)((gu / kSB) & 1))) return;
         float v[kKPT];
 #pragma unroll
         for (int i = 0; i < kKPT; ++i) v[i] = 0.f;
-        const float* src = sp + (size_t)buf * kGroupWarps * 16 * kSpLd + r * kSpLd + kKPT * c8;
+        const float* src = sp + (size_t)sb * kGroupWarps * 16 * kSpLd + r * kSpLd + kKPT * c8;
 #pragma unroll
         for (int w = 0; w < kGroupWarps; ++w) {
           if constexpr (kKPT == 4) {
@@ -403,7 +412,7 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
         __threadfence_block();
         asm volatile("bar.sync 1, %0;" ::"n"(SW * 32) : "memory");     // partials consumed; P, corr, l written
         if (t == 0) {
-          mbar_arrive(sempty_bar(buf));
+          mbar_arrive(sempty_bar(sb));
           mbar_arrive(pfull_bar(buf));
         }
       }
