@@ -142,6 +142,16 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ uint32_t ldg_nc_pinned(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_u8_pinned(const unsigned char* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -231,7 +241,10 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
       if (++pf_chunk == nchunks) { pf_chunk = 0; pf_crop = next_active(pf_crop + (int)gridDim.x); }
     };
     if (kPrefetch > 0) for (int i = 0; i < kPrefetch; ++i) prefetch_next();
-    for (int cb = first; cb < n; cb = next_active(cb + (int)gridDim.x)) {
+    for (int cb = first, cand = 0, cand_fin = 0; cb < n; cb = cand_fin ? next_active(cand) : cand) {
+      // the next candidate's finished[] flag is requested now and looked at when this crop is done (see the score group)
+      cand = cb + (int)gridDim.x;
+      cand_fin = (finished != nullptr && cand < n) ? (int)ldg_u8_pinned(finished + crop_of(cand)) : 0;
       for (int c = 0; c < nchunks; ++c, ++gi) {
         const int stage = gi % kNS;
         if (kPrefetch > 0) prefetch_next();
@@ -259,10 +272,12 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
       const bool lo = g < heads, hi = g + 8 < heads;
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
-        dst[ks][0] = lo ? __ldg(r_lo + ks * 8) : 0u;
-        dst[ks][1] = hi ? __ldg(r_hi + ks * 8) : 0u;
-        dst[ks][2] = lo ? __ldg(r_lo + ks * 8 + 4) : 0u;
-        dst[ks][3] = hi ? __ldg(r_hi + ks * 8 + 4) : 0u;
+        // volatile asm: a plain __ldg is sunk to its first use (ncu: the score warps spent 14 % of their time on that
+        // round trip at every crop boundary); these stay where they are written, one crop ahead of their use
+        dst[ks][0] = lo ? ldg_nc_pinned(r_lo + ks * 8) : 0u;
+        dst[ks][1] = hi ? ldg_nc_pinned(r_hi + ks * 8) : 0u;
+        dst[ks][2] = lo ? ldg_nc_pinned(r_lo + ks * 8 + 4) : 0u;
+        dst[ks][3] = hi ? ldg_nc_pinned(r_hi + ks * 8 + 4) : 0u;
       }
     };
     int gu = 0;
@@ -271,11 +286,18 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
     for (int cb = first; cb < n;) {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) { qa[ks][0] = qn[ks][0]; qa[ks][1] = qn[ks][1]; qa[ks][2] = qn[ks][2]; qa[ks][3] = qn[ks][3]; }
-      const int cb_next = next_active(cb + (int)gridDim.x);
-      if (cb_next < n) load_q(qn, cb_next);
-      cb = cb_next;
+      // Which crop comes next depends on finished[] -- a dependent round trip at every crop boundary (ncu: 14 % of the
+      // score warps' time): the flag of the next candidate is requested here and looked at after the first chunk.
+      const int cand = cb + (int)gridDim.x;
+      uint32_t cand_fin = 0;
+      if (finished != nullptr && cand < n) cand_fin = ldg_u8_pinned(finished + crop_of(cand));
+      int cb_next = cand;
 
       for (int c = 0; c < nchunks; ++c, ++gu) {
+        if (c == 1 || (c == 0 && nchunks == 1)) {
+          if (cand_fin != 0) cb_next = next_active(cand);
+          if (cb_next < n) load_q(qn, cb_next);
+        }
         const int stage = gu % kNS, sb = gu % kSB;
         const uint32_t sbase = stage0 + stage * C::kStageBytes;
         if (!mbar_wait(full_bar(stage), (uint32_t)((gu / kNS) & 1))) return;
@@ -309,12 +331,16 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
           mbar_arrive(empty_bar(stage));
         }
       }
+      cb = cb_next;
     }
   } else if (warp < 2 * kGroupWarps) {
     // =============================================================== context group: C = corr * C + P X^
     const int cw = warp - kGroupWarps;
     int gu = 0;
-    for (int cb = first; cb < n; cb = next_active(cb + (int)gridDim.x)) {
+    for (int cb = first, cand = 0, cand_fin = 0; cb < n; cb = cand_fin ? next_active(cand) : cand) {
+      // the next candidate's finished[] flag is requested now and looked at when this crop is done (see the score group)
+      cand = cb + (int)gridDim.x;
+      cand_fin = (finished != nullptr && cand < n) ? (int)ldg_u8_pinned(finished + crop_of(cand)) : 0;
       float acc[NT][4];
 #pragma unroll
       for (int i = 0; i < NT; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
@@ -363,7 +389,10 @@ cross_absorbed_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ xn, 
     const int t = tid - 2 * kGroupWarps * 32;
     const int r = t >> 3, c8 = t & 7;
     int gu = 0;
-    for (int cb = first; cb < n; cb = next_active(cb + (int)gridDim.x)) {
+    for (int cb = first, cand = 0, cand_fin = 0; cb < n; cb = cand_fin ? next_active(cand) : cand) {
+      // the next candidate's finished[] flag is requested now and looked at when this crop is done (see the score group)
+      cand = cb + (int)gridDim.x;
+      cand_fin = (finished != nullptr && cand < n) ? (int)ldg_u8_pinned(finished + crop_of(cand)) : 0;
       float m_run = -INFINITY, l_run = 0.f;      // softmax state of row r (replicated over its 8 threads)
       for (int c = 0; c < nchunks; ++c, ++gu) {
         const int buf = gu & 1, sb = gu % kSB;
