@@ -17,7 +17,14 @@
 // stand-alone launches), optionally followed by a LayerNorm tail: once all n-tiles of a row block are stored, each of
 // the block's CTAs normalises its share of the 128 rows (same arithmetic as layernorm.cu).
 // Tiles of a stage: tile t -> CTA t % gridDim; all CTAs are co-resident (grid <= SM count, 1 CTA / SM), so a spin wait
-// on another CTA's counter always ends.  Counters: [stage][kind][row block], zeroed by the caller before the launch.
+// on another CTA's counter always ends.  Counters: [stage][kind][row block], one 128-byte line each, zeroed by the
+// caller before the launch.
+//
+// MEASURED (B200, 1024 crops, profiles/r02_gemm_seq.txt): bit-identical to the separate launches and SLOWER -- decoder
+// alone 94.6 vs 86.6 ms.  The hand-over is cheap (0.4-1.1 us from "rows published" to the next stage's first operands)
+// and every fused stage saves ~3 us, but publishing a tile costs the epilogue + a GPU-scope release (2.3-3 us), the
+// LayerNorm tail 4-5 us, and a stage here is ~5 us slower than the stand-alone kernel + LayerNorm launch.  Opt-in
+// (EC_SEQ=1 / option "decode_seq"); kept with its bit-identity test and the in-kernel stage clocks (-DEC_SEQ_TIMING).
 #pragma once
 #include "gemm_kernel.cuh"
 
