@@ -112,8 +112,9 @@ class OracleCoCa:
         x = images.reshape(B, C, H // P, P, W // P, P).permute(0, 2, 4, 1, 3, 5)
         return x.reshape(B, (H // P) * (W // P), C * P * P)
 
-    def encode_image_tokens(self, images: torch.Tensor):
-        """coca_model.py:152-155 `_encode_image` (normalize=True) -> (image_latent [B,E], image_embs [B,255,E])."""
+    def vision_trunk(self, images: torch.Tensor) -> torch.Tensor:
+        """Patch embedding + class token + positions + ln_pre + the ViT blocks: the tokens [B, 1 + G*G, W] that the
+        attentional pooler reads (pinned against transformers' CLIPVisionModel in tests/test_oracle_pins.py)."""
         cfg, sd = self.cfg, self.sd
         images = _r(images.to(torch.float32), self.emu)
         x = self._lin(self.patchify(images), sd["visual.conv1.weight"].reshape(cfg.vision_width, -1))
@@ -122,6 +123,12 @@ class OracleCoCa:
         x = self._ln(x, "visual.ln_pre")
         for i in range(cfg.vision_layers):
             x = self._block(x, f"visual.transformer.resblocks.{i}", cfg.vision_heads)
+        return x
+
+    def encode_image_tokens(self, images: torch.Tensor):
+        """coca_model.py:152-155 `_encode_image` (normalize=True) -> (image_latent [B,E], image_embs [B,255,E])."""
+        cfg, sd = self.cfg, self.sd
+        x = self.vision_trunk(images)
         # AttentionalPooler: q = ln_q(query) (input independent), k = v = ln_k(x)
         E = cfg.embed_dim
         kx = self._ln(x, "visual.attn_pool.ln_k")

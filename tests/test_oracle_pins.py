@@ -247,3 +247,90 @@ def test_generate_loop_matches_hf_processors_and_multinomial(tiny, fixed):
             assert (a[fin] - b[fin]).abs().max().item() <= (1e-4 if mode == "kvcache" else 0.0)
     ends = ((text == eos) | (text == pad)).float().argmax(dim=1)
     assert len(set(ends.tolist())) > 1, "test set-up: rows should stop at different steps"
+
+
+def test_vision_trunk_matches_transformers_clip_vision_model():
+    """The WIRING of the image tower's trunk -- patch conv without bias, class token first, learned positions, ln_pre,
+    pre-LN blocks with erf-GELU MLPs -- against an independent third-party implementation of the same published
+    architecture: transformers' `CLIPVisionModel` (the OpenAI CLIP ViT that open_clip's `VisionTransformer`
+    re-implements; `hidden_act="gelu"` as in open_clip's CoCa configs) loaded with the oracle's weights.  Its
+    `last_hidden_state` is the trunk output before any post-norm, i.e. what the attentional pooler reads."""
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    cfg = get_config("coca_tiny")
+    sd = synth.make_state_dict(cfg, seed=31)
+    W, L = cfg.vision_width, cfg.vision_layers
+    hf_cfg = CLIPVisionConfig(hidden_size=W, intermediate_size=4 * W, num_hidden_layers=L,
+                              num_attention_heads=cfg.vision_heads, image_size=cfg.image_size, patch_size=cfg.patch_size,
+                              hidden_act="gelu", layer_norm_eps=1e-5, attention_dropout=0.0)
+    hf = CLIPVisionModel(hf_cfg).eval()
+    m = {"vision_model.embeddings.class_embedding": sd["visual.class_embedding"],
+         "vision_model.embeddings.patch_embedding.weight": sd["visual.conv1.weight"],
+         "vision_model.embeddings.position_embedding.weight": sd["visual.positional_embedding"],
+         "vision_model.pre_layrnorm.weight": sd["visual.ln_pre.weight"],
+         "vision_model.pre_layrnorm.bias": sd["visual.ln_pre.bias"]}
+    for i in range(L):
+        src, dst = f"visual.transformer.resblocks.{i}.", f"vision_model.encoder.layers.{i}."
+        w_in, b_in = sd[src + "attn.in_proj_weight"], sd[src + "attn.in_proj_bias"]
+        for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
+            m[dst + f"self_attn.{nm}.weight"] = w_in[j * W:(j + 1) * W]
+            m[dst + f"self_attn.{nm}.bias"] = b_in[j * W:(j + 1) * W]
+        m[dst + "self_attn.out_proj.weight"] = sd[src + "attn.out_proj.weight"]
+        m[dst + "self_attn.out_proj.bias"] = sd[src + "attn.out_proj.bias"]
+        for a, b in (("ln_1", "layer_norm1"), ("ln_2", "layer_norm2"), ("mlp.c_fc", "mlp.fc1"), ("mlp.c_proj", "mlp.fc2")):
+            m[dst + b + ".weight"] = sd[src + a + ".weight"]
+            m[dst + b + ".bias"] = sd[src + a + ".bias"]
+    own = hf.state_dict()
+    missing = [k for k in own if k not in m and "post_layernorm" not in k and "position_ids" not in k]
+    assert not missing, missing
+    hf.load_state_dict({k: v.clone().float() for k, v in m.items()}, strict=False)
+    g = torch.Generator().manual_seed(5)
+    images = torch.randn((3, 3, cfg.image_size, cfg.image_size), generator=g)
+    with torch.no_grad():
+        ref = hf(pixel_values=images).last_hidden_state
+    got = OracleCoCa(cfg, sd).vision_trunk(images)
+    assert got.shape == ref.shape
+    err = (got - ref).abs().max().item()
+    assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
+
+
+def test_text_tower_matches_transformers_clip_text_model():
+    """The unimodal text tower's trunk (token + position embeddings, causal pre-LN blocks) against transformers'
+    `CLIPTextModel` -- the OpenAI CLIP text transformer that open_clip's `TextTransformer` re-implements -- loaded with
+    the oracle's weights: the hidden states BEFORE the final LayerNorm are the token rows the multimodal decoder reads
+    (`tokens = x[:, :-1]`; the appended CLS token is last, so under the causal mask no token row depends on it)."""
+    from transformers import CLIPTextConfig, CLIPTextModel
+    cfg = get_config("coca_tiny")
+    sd = synth.make_state_dict(cfg, seed=32)
+    W, L = cfg.text_width, cfg.text_layers
+    n_pos = sd["text.positional_embedding"].shape[0]
+    hf_cfg = CLIPTextConfig(vocab_size=cfg.vocab_size, hidden_size=W, intermediate_size=4 * W, num_hidden_layers=L,
+                            num_attention_heads=cfg.text_heads, max_position_embeddings=n_pos, hidden_act="gelu",
+                            layer_norm_eps=1e-5, attention_dropout=0.0, eos_token_id=cfg.eos_token_id,
+                            bos_token_id=cfg.sot_token_id, pad_token_id=cfg.pad_token_id)
+    hf = CLIPTextModel(hf_cfg).eval()
+    m = {"text_model.embeddings.token_embedding.weight": sd["text.token_embedding.weight"],
+         "text_model.embeddings.position_embedding.weight": sd["text.positional_embedding"],
+         "text_model.final_layer_norm.weight": sd["text.ln_final.weight"],
+         "text_model.final_layer_norm.bias": sd["text.ln_final.bias"]}
+    for i in range(L):
+        src, dst = f"text.transformer.resblocks.{i}.", f"text_model.encoder.layers.{i}."
+        w_in, b_in = sd[src + "attn.in_proj_weight"], sd[src + "attn.in_proj_bias"]
+        for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
+            m[dst + f"self_attn.{nm}.weight"] = w_in[j * W:(j + 1) * W]
+            m[dst + f"self_attn.{nm}.bias"] = b_in[j * W:(j + 1) * W]
+        m[dst + "self_attn.out_proj.weight"] = sd[src + "attn.out_proj.weight"]
+        m[dst + "self_attn.out_proj.bias"] = sd[src + "attn.out_proj.bias"]
+        for a, b in (("ln_1", "layer_norm1"), ("ln_2", "layer_norm2"), ("mlp.c_fc", "mlp.fc1"), ("mlp.c_proj", "mlp.fc2")):
+            m[dst + b + ".weight"] = sd[src + a + ".weight"]
+            m[dst + b + ".bias"] = sd[src + a + ".bias"]
+    missing = [k for k in hf.state_dict() if k not in m and "position_ids" not in k]
+    assert not missing, missing
+    hf.load_state_dict({k: v.clone().float() for k, v in m.items()}, strict=False)
+    g = torch.Generator().manual_seed(6)
+    text = torch.randint(1, cfg.vocab_size - 2, (4, 9), generator=g)
+    with torch.no_grad():
+        ref = hf(input_ids=text, output_hidden_states=True).hidden_states[-1]
+    got = OracleCoCa(cfg, sd).text_tokens(text)
+    assert got.shape == ref.shape
+    err = (got - ref).abs().max().item()
+    assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
