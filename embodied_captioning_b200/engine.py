@@ -52,7 +52,19 @@ class CaptionEngine:
     def caption_frames(self, frames: torch.Tensor, rects: torch.Tensor, frame_idx: torch.Tensor,
                        flags: Optional[torch.Tensor], keys: Optional[torch.Tensor], seq_len: int = 30,
                        min_seq_len: int = 5, mode: int = ops.MODE_FULL_MEAN_1MINUS):
-        """frames uint8 [F,H,W,3], rects int32 [N,4], frame_idx int32 [N] (all on device)."""
+        """frames uint8 [F,H,W,3], rects int32 [N,4], frame_idx int32 [N] (all on device).  N = 0 (a frame without
+        detections: the reference's per-box loops simply do not run, goal_exploration.py:95-105) returns empty tensors
+        without touching the GPU path."""
+        if rects.shape[0] == 0:
+            dev = self.device
+            out = {"tokens": torch.zeros((0, seq_len), dtype=torch.int64, device=dev),
+                   "latent": torch.zeros((0, self.cfg.embed_dim), dtype=torch.float32, device=dev),
+                   "status": torch.zeros((0,), dtype=torch.int32, device=dev)}
+            if keys is not None:
+                out.update(inst_keys=torch.zeros((0,), dtype=torch.int64, device=dev),
+                           inst_scores=torch.zeros((0,), dtype=torch.float32, device=dev),
+                           inst_counts=torch.zeros((0,), dtype=torch.int32, device=dev))
+            return out
         x, _, status = ops.preprocess_crops(frames, rects, frame_idx, flags, size=self.cfg.image_size)
         out = self.caption_preprocessed(x, keys, seq_len, min_seq_len, mode)
         out["status"] = status

@@ -253,3 +253,18 @@ def test_evaluate_csv_end_to_end_vs_reference_loop(device, tmp_path):
     assert same == len(rows), f"{same}/{len(rows)} captions identical to the reference loop"
     with pytest.raises(ValueError):
         create_model("coca_small", precision="int8")
+
+
+@pytest.mark.gpu
+def test_frame_without_detections_returns_empty_results(device):
+    """A frame with no boxes (the reference's per-box loops do not run, goal_exploration.py:95-105): empty tensors of
+    the right shapes and dtypes, no native call; a single crop and a single-view instance still work."""
+    sd = synth.make_state_dict(get_config("coca_tiny"), seed=3)
+    eng = CaptionEngine("coca_tiny", None, device=device, decode_graph=True, state_dict=sd)
+    frames = torch.zeros((1, 48, 64, 3), dtype=torch.uint8, device=device)
+    out = eng.caption_boxes(frames, np.zeros((0, 4), np.float32), np.zeros((0,), np.int32), keys=np.zeros((0,), np.int64))
+    assert out["tokens"].shape == (0, 30) and out["latent"].shape[0] == 0 and out["status"].numel() == 0
+    assert out["inst_keys"].numel() == 0 and out["inst_scores"].numel() == 0 and out["inst_counts"].numel() == 0
+    one = eng.caption_boxes(frames, np.array([[4, 4, 40, 40]], np.float32), np.zeros((1,), np.int32), keys=np.array([7], np.int64))
+    ops.check_watchdog(device)
+    assert one["tokens"].shape == (1, 30) and one["inst_keys"].cpu().tolist() == [7] and one["inst_counts"].cpu().tolist() == [1]
