@@ -518,7 +518,10 @@ static int launch_xa_sw(const bf16* qp, const bf16* xn, bf16* ctx, int n, int he
     EC_CHECK_CUDA(cudaFuncSetAttribute(xa::cross_absorbed_kernel<T, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
     attr_done[dev] = true;
   }
-  const int grid = std::min(n, num_sms());
+  // EC_XA_MAX_CTAS (probe): fewer CTAs than SMs leave room for another row chain's GEMMs next to this stream
+  static const int env_cap = [] { const char* e = getenv("EC_XA_MAX_CTAS"); return e ? atoi(e) : 0; }();
+  int grid = std::min(n, num_sms());
+  if (env_cap > 0) grid = std::min(grid, env_cap);
   note_launches(1);
   EC_CHECK_CUDA(launch_small_kernel(xa::cross_absorbed_kernel<T, SW>, dim3(grid), dim3(xa::kThreadsOf<SW>), (size_t)C::kSmem, stream,
                                     qp, xn, ctx, n, heads, n_kv, finished, st, reverse));
